@@ -1,0 +1,717 @@
+// C ABI of the B200 front-end (include/cwsl_b200.h): receiver handles, slot groups, IQ ring,
+// phase-table cache and launch orchestration. No compute happens on the host: every sample is
+// produced by the kernels in cwsl_kernels.cu; if CUDA is unavailable the entry points fail.
+#include "../../include/cwsl_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "cwsl_kernels.hpp"
+#include "cwsl_tables.hpp"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(e__ == cudaErrorMemoryAllocation ? CWSL_ERR_NOMEM : CWSL_ERR_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e__));                                                       \
+    } while (0)
+
+// ---- per-device shared state: constant taps + phase-table cache ---------------------------------
+struct PhaseKey {
+    int device;
+    uint32_t fs;
+    int32_t freq;
+    int usb;
+    uint32_t length;
+    bool operator<(const PhaseKey& o) const {
+        return std::tie(device, fs, freq, usb, length) < std::tie(o.device, o.fs, o.freq, o.usb, o.length);
+    }
+};
+struct PhaseEntry {
+    float2* table = nullptr;
+    int refs = 0;
+};
+std::mutex g_mu;
+std::map<PhaseKey, PhaseEntry> g_phase_cache;
+std::set<std::pair<int, uint32_t>> g_taps_uploaded;
+
+struct ChannelHost {
+    int32_t demod_freq = 0;
+    int usb = 1;
+    float scale = 1.0f;
+    cwsl::NcoTables nco;
+};
+
+struct Group {
+    double period = 0;
+    size_t af_size = 0;
+    size_t af_stride = 0;
+    std::vector<ChannelHost> ch;
+    std::vector<PhaseKey> phase_keys;
+    // device
+    float2* d_tone = nullptr;
+    const float2** d_phase = nullptr;
+    float* d_sign = nullptr;
+    float* d_scale = nullptr;
+    unsigned* d_maxbits = nullptr;
+    float* d_factor = nullptr;
+    float* d_maxval = nullptr;
+    float* d_audio = nullptr;
+    int16_t* d_out = nullptr;
+    // slot state (units: SSBD blocks unless noted)
+    uint64_t slot_start = 0;   // absolute index of the slot's block 0
+    uint64_t processed = 0;    // slot-relative blocks already demodulated
+    uint64_t iq_blocks = 0;    // IQ blocks pushed since the slot edge
+    size_t last_write_index = 0;
+    bool have_result = false;
+};
+
+}  // namespace
+
+struct cwsl_rx {
+    int device = 0;
+    uint32_t fs = 0, iq_len = 0;
+    cwsl::SsbdGeometry geo;
+    uint32_t sub = 0;  // SSBD blocks per IQ block
+    int mode = CWSL_MODE_FAST;
+    double ring_seconds = 0;
+    cudaStream_t stream = nullptr;
+    float2* d_ring = nullptr;        // owned ring (nullptr while bound to external IQ)
+    const float2* ring_ptr = nullptr;  // what the kernels read
+    uint32_t ring_blocks = 0;
+    uint64_t abs_written = 0;  // SSBD blocks pushed since creation
+    bool bound = false;
+    bool committed = false;
+    std::vector<Group> groups;
+    // timing
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_demod, ev_quant;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+cudaEvent_t get_event(cwsl_rx* rx) {
+    if (!rx->ev_pool.empty()) {
+        cudaEvent_t e = rx->ev_pool.back();
+        rx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void free_group_device(Group& g) {
+    cudaFree(g.d_tone);
+    cudaFree((void*)g.d_phase);
+    cudaFree(g.d_sign);
+    cudaFree(g.d_scale);
+    cudaFree(g.d_maxbits);
+    cudaFree(g.d_factor);
+    cudaFree(g.d_maxval);
+    cudaFree(g.d_audio);
+    cudaFree(g.d_out);
+    g.d_tone = nullptr;
+    g.d_phase = nullptr;
+    g.d_sign = g.d_scale = g.d_factor = g.d_maxval = g.d_audio = nullptr;
+    g.d_maxbits = nullptr;
+    g.d_out = nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (const PhaseKey& k : g.phase_keys) {
+        auto it = g_phase_cache.find(k);
+        if (it != g_phase_cache.end() && --it->second.refs <= 0) {
+            cudaFree(it->second.table);
+            g_phase_cache.erase(it);
+        }
+    }
+    g.phase_keys.clear();
+}
+
+// Upload tables, build missing phase tables, allocate audio buffers. Idempotent.
+int commit(cwsl_rx* rx) {
+    if (rx->committed) return CWSL_OK;
+    if (rx->groups.empty()) return fail(CWSL_ERR_STATE, "no slot group defined");
+    // constant-bank taps (once per device and block size), cross-checked against the baked copy
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        const auto key = std::make_pair(rx->device, rx->geo.block_size);
+        if (!g_taps_uploaded.count(key)) {
+            const std::vector<float> h = cwsl::lowpass_taps(rx->geo);
+            const float* baked = cwsl::baked_taps_transposed(rx->geo.block_size);
+            if (!baked) return fail(CWSL_ERR_INVALID, "unsupported block size %u", rx->geo.block_size);
+            for (uint32_t m = 0; m < rx->geo.block_size; ++m)
+                for (uint32_t n = 0; n < 32; ++n)
+                    if (std::memcmp(&baked[m * 32 + n], &h[rx->geo.block_size * n + m], sizeof(float)) != 0)
+                        return fail(CWSL_ERR_STATE,
+                                    "baked low-pass taps differ from this host's libm result at tap %u "
+                                    "(rebuild: make -C cwsl_digi_b200/csrc taps all)",
+                                    rx->geo.block_size * n + m);
+            CK(cwsl::upload_taps(rx->geo.block_size, h.data()));
+            g_taps_uploaded.insert(key);
+        }
+    }
+    uint64_t max_blocks = 0;
+    for (Group& g : rx->groups) {
+        const uint32_t C = (uint32_t)g.ch.size();
+        if (C == 0) return fail(CWSL_ERR_STATE, "slot group without channels");
+        const uint32_t BS = rx->geo.block_size;
+        g.af_stride = (g.af_size + 7) / 8 * 8;
+        max_blocks = std::max<uint64_t>(max_blocks, g.af_size);
+        std::vector<float2> tone((size_t)C * BS);
+        std::vector<float> sign(C), scale(C);
+        for (uint32_t c = 0; c < C; ++c) {
+            for (uint32_t m = 0; m < BS; ++m)
+                tone[(size_t)c * BS + m] = make_float2(g.ch[c].nco.tone[m].real(), g.ch[c].nco.tone[m].imag());
+            sign[c] = g.ch[c].nco.sign;
+            scale[c] = g.ch[c].scale;
+        }
+        CK(cudaMalloc(&g.d_tone, tone.size() * sizeof(float2)));
+        CK(cudaMalloc((void**)&g.d_phase, C * sizeof(float2*)));
+        CK(cudaMalloc(&g.d_sign, C * sizeof(float)));
+        CK(cudaMalloc(&g.d_scale, C * sizeof(float)));
+        CK(cudaMalloc(&g.d_maxbits, C * sizeof(unsigned)));
+        CK(cudaMalloc(&g.d_factor, C * sizeof(float)));
+        CK(cudaMalloc(&g.d_maxval, C * sizeof(float)));
+        CK(cudaMalloc(&g.d_audio, (size_t)C * g.af_stride * sizeof(float)));
+        CK(cudaMalloc(&g.d_out, (size_t)C * g.af_size * sizeof(int16_t)));
+        CK(cudaMemcpyAsync(g.d_tone, tone.data(), tone.size() * sizeof(float2), cudaMemcpyHostToDevice, rx->stream));
+        CK(cudaMemcpyAsync(g.d_sign, sign.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
+        CK(cudaMemcpyAsync(g.d_scale, scale.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
+        CK(cudaMemsetAsync(g.d_maxbits, 0, C * sizeof(unsigned), rx->stream));
+        CK(cudaStreamSynchronize(rx->stream));  // host vectors go out of scope
+
+        // phase tables: one per distinct (Fs, demodFreq, sideband, length), shared process-wide
+        const uint32_t length = (uint32_t)((g.af_size + 3) / 4 * 4 + 4);
+        std::vector<const float2*> ptrs(C);
+        std::vector<float2> new_inc;
+        std::vector<float2*> new_tab;
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            for (uint32_t c = 0; c < C; ++c) {
+                PhaseKey k{rx->device, rx->fs, g.ch[c].demod_freq, g.ch[c].usb, length};
+                PhaseEntry& e = g_phase_cache[k];
+                if (!e.table) {
+                    cudaError_t err = cudaMalloc(&e.table, (size_t)length * sizeof(float2));
+                    if (err != cudaSuccess) {
+                        g_phase_cache.erase(k);
+                        return fail(CWSL_ERR_NOMEM, "phase table alloc: %s", cudaGetErrorString(err));
+                    }
+                    new_inc.push_back(make_float2(g.ch[c].nco.phase_inc.real(), g.ch[c].nco.phase_inc.imag()));
+                    new_tab.push_back(e.table);
+                }
+                ++e.refs;
+                g.phase_keys.push_back(k);
+                ptrs[c] = e.table;
+            }
+        }
+        CK(cudaMemcpy((void*)g.d_phase, ptrs.data(), C * sizeof(float2*), cudaMemcpyHostToDevice));
+        if (!new_tab.empty()) {
+            float2* d_inc = nullptr;
+            float2** d_tab = nullptr;
+            CK(cudaMalloc(&d_inc, new_inc.size() * sizeof(float2)));
+            CK(cudaMalloc((void**)&d_tab, new_tab.size() * sizeof(float2*)));
+            CK(cudaMemcpy(d_inc, new_inc.data(), new_inc.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy((void*)d_tab, new_tab.data(), new_tab.size() * sizeof(float2*), cudaMemcpyHostToDevice));
+            CK(cwsl::launch_phase_tables(d_inc, d_tab, (uint32_t)new_tab.size(), length, rx->stream));
+            CK(cudaStreamSynchronize(rx->stream));
+            cudaFree(d_inc);
+            cudaFree((void*)d_tab);
+        }
+    }
+    // IQ ring
+    if (!rx->bound) {
+        double secs = rx->ring_seconds;
+        uint64_t blocks;
+        if (secs > 0)
+            blocks = (uint64_t)(secs * rx->fs / rx->geo.block_size);
+        else
+            blocks = max_blocks + 64;  // longest slot (+5 s) fits without intermediate demodulation
+        const uint64_t quantum = std::max<uint64_t>(rx->sub, 4);
+        blocks = std::max<uint64_t>(blocks, 4 * (uint64_t)rx->sub + 64);
+        blocks = (blocks + quantum - 1) / quantum * quantum;
+        rx->ring_blocks = (uint32_t)blocks;
+        CK(cudaMalloc(&rx->d_ring, (size_t)blocks * rx->geo.block_size * sizeof(float2)));
+        rx->ring_ptr = rx->d_ring;
+    }
+    rx->committed = true;
+    return CWSL_OK;
+}
+
+// SSBD blocks of the current slot that are accepted by the reference's af-buffer guard.
+uint64_t slot_target_blocks(const cwsl_rx* rx, const Group& g) {
+    const size_t acc = cwsl::accepted_blocks((size_t)g.iq_blocks, rx->iq_len, rx->geo.dec_ratio, g.af_size);
+    return (uint64_t)acc * rx->sub;
+}
+
+int process_group(cwsl_rx* rx, Group& g) {
+    const uint64_t target = slot_target_blocks(rx, g);
+    if (target <= g.processed) return CWSL_OK;
+    // history still in the ring?
+    const uint64_t first_needed = g.slot_start + (g.processed >= 31 ? g.processed - 31 : 0);
+    if (rx->abs_written - first_needed > rx->ring_blocks)
+        return fail(CWSL_ERR_OVERRUN, "IQ ring overrun: slot needs block %llu, ring holds the last %u",
+                    (unsigned long long)first_needed, rx->ring_blocks);
+    cwsl::DemodLaunch p;
+    p.iq_ring = rx->ring_ptr;
+    p.ring_blocks = rx->ring_blocks;
+    p.ring_off = (uint32_t)(g.slot_start % rx->ring_blocks);
+    p.block_size = rx->geo.block_size;
+    p.b0 = (uint32_t)g.processed;
+    p.b1 = (uint32_t)target;
+    p.n_channels = (uint32_t)g.ch.size();
+    p.tone = g.d_tone;
+    p.phase = g.d_phase;
+    p.sign = g.d_sign;
+    p.audio = g.d_audio;
+    p.af_stride = g.af_stride;
+    p.maxbits = g.d_maxbits;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (rx->timing) {
+        e0 = get_event(rx);
+        e1 = get_event(rx);
+        CK(cudaEventRecord(e0, rx->stream));
+    }
+    if (rx->mode == CWSL_MODE_EXACT)
+        CK(cwsl::launch_demod_exact(p, rx->stream));
+    else
+        CK(cwsl::launch_demod_fast(p, rx->stream));
+    if (rx->timing) {
+        CK(cudaEventRecord(e1, rx->stream));
+        rx->ev_demod.emplace_back(e0, e1);
+    }
+    g.processed = target;
+    return CWSL_OK;
+}
+
+int push_common(cwsl_rx* rx, const float* iq, size_t n_blocks, cudaMemcpyKind kind) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    if (n_blocks == 0) return CWSL_OK;
+    if (!iq) return fail(CWSL_ERR_INVALID, "null IQ pointer");
+    DeviceGuard dg(rx->device);
+    if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
+    if (rx->bound) return fail(CWSL_ERR_STATE, "receiver is bound to an external IQ buffer");
+    int rc = commit(rx);
+    if (rc != CWSL_OK) return rc;
+    const uint32_t BS = rx->geo.block_size;
+    // never let a single copy cover more than half the ring, so open slots can be drained first
+    const size_t max_chunk = std::max<size_t>(1, (rx->ring_blocks / 2) / rx->sub);
+    size_t done = 0;
+    while (done < n_blocks) {
+        const size_t nb = std::min(max_chunk, n_blocks - done);
+        const uint64_t add = (uint64_t)nb * rx->sub;
+        // demodulate any slot whose un-demodulated samples (plus 31 blocks of history) would be overwritten
+        for (Group& g : rx->groups) {
+            const uint64_t first_needed = g.slot_start + (g.processed >= 31 ? g.processed - 31 : 0);
+            if (rx->abs_written + add - first_needed > rx->ring_blocks) {
+                rc = process_group(rx, g);
+                if (rc != CWSL_OK) return rc;
+            }
+        }
+        const uint64_t row = rx->abs_written % rx->ring_blocks;
+        const uint64_t first = std::min<uint64_t>(add, rx->ring_blocks - row);
+        const float* src = iq + done * (size_t)rx->iq_len * 2;
+        CK(cudaMemcpyAsync(rx->d_ring + row * BS, src, first * BS * sizeof(float2), kind, rx->stream));
+        if (first < add)
+            CK(cudaMemcpyAsync(rx->d_ring, src + first * BS * 2, (add - first) * BS * sizeof(float2), kind, rx->stream));
+        rx->abs_written += add;
+        for (Group& g : rx->groups) g.iq_blocks += nb;
+        done += nb;
+    }
+    return CWSL_OK;
+}
+
+Group* get_group(cwsl_rx* rx, int group) {
+    if (!rx || group < 0 || group >= (int)rx->groups.size()) {
+        fail(CWSL_ERR_INVALID, "bad receiver/group %d", group);
+        return nullptr;
+    }
+    return &rx->groups[group];
+}
+
+}  // namespace
+
+extern "C" {
+
+int cwsl_abi_version(void) { return CWSL_B200_ABI_VERSION; }
+
+const char* cwsl_last_error(void) { return g_last_error.c_str(); }
+
+int cwsl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int cwsl_ssbd_params(uint32_t sample_rate, uint32_t out[9]) {
+    cwsl::SsbdGeometry g;
+    if (!cwsl::ssbd_geometry(sample_rate, &g)) return fail(CWSL_ERR_INVALID, "Fs/B must be an even integer >= 4");
+    out[0] = g.fs;
+    out[1] = 2 * cwsl::kSSBBW;
+    out[2] = g.in_size;
+    out[3] = 4;
+    out[4] = cwsl::kSSBBW;
+    out[5] = 1u << cwsl::kLatencyLog2;
+    out[6] = g.filt_order;
+    out[7] = g.block_size;
+    out[8] = g.num_ws;
+    return CWSL_OK;
+}
+
+int cwsl_build_tables(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, float* filter, float* tone,
+                      float* phase_inc) {
+    cwsl::SsbdGeometry g;
+    if (!cwsl::ssbd_geometry(sample_rate, &g)) return fail(CWSL_ERR_INVALID, "Fs/B must be an even integer >= 4");
+    cwsl::NcoTables t;
+    if (!cwsl::nco_tables(g, demod_freq_hz, is_usb != 0, &t)) return fail(CWSL_ERR_INVALID, "Signal outside of band");
+    const std::vector<float> h = cwsl::lowpass_taps(g);
+    if (filter) std::memcpy(filter, h.data(), h.size() * sizeof(float));
+    if (tone)
+        for (uint32_t n = 0; n < g.block_size; ++n) {
+            tone[2 * n] = t.tone[n].real();
+            tone[2 * n + 1] = t.tone[n].imag();
+        }
+    if (phase_inc) {
+        phase_inc[0] = t.phase_inc.real();
+        phase_inc[1] = t.phase_inc.imag();
+    }
+    return CWSL_OK;
+}
+
+size_t cwsl_af_size(double period_s) { return cwsl::af_size(static_cast<float>(period_s)); }
+
+size_t cwsl_accepted_blocks(size_t n_iq_blocks, uint32_t iq_len, uint32_t sample_rate, size_t af_size) {
+    if (sample_rate < cwsl::kWaveSR || iq_len == 0 || af_size == 0) return 0;
+    return cwsl::accepted_blocks(n_iq_blocks, iq_len, sample_rate / cwsl::kWaveSR, af_size);
+}
+
+cwsl_rx_t* cwsl_rx_create(int device, uint32_t sample_rate, uint32_t iq_len, double ring_seconds) {
+    cwsl::SsbdGeometry geo;
+    if (!cwsl::ssbd_geometry(sample_rate, &geo)) {
+        fail(CWSL_ERR_INVALID, "Fs/B must be an even integer >= 4 (Fs=%u)", sample_rate);
+        return nullptr;
+    }
+    if (geo.block_size != 16 && geo.block_size != 8 && geo.block_size != 4) {
+        fail(CWSL_ERR_INVALID, "unsupported sample rate %u (supported: 48000, 96000, 192000)", sample_rate);
+        return nullptr;
+    }
+    if (iq_len == 0 || iq_len % geo.in_size != 0) {
+        fail(CWSL_ERR_INVALID, "iq_len %u must be a positive multiple of SSBD::GetInSize() = %u", iq_len, geo.in_size);
+        return nullptr;
+    }
+    if (ring_seconds < 0) {
+        fail(CWSL_ERR_INVALID, "ring_seconds < 0");
+        return nullptr;
+    }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        fail(CWSL_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        fail(CWSL_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+        return nullptr;
+    }
+    DeviceGuard dg(device);
+    if (!dg.ok) {
+        fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+        return nullptr;
+    }
+    std::unique_ptr<cwsl_rx> rx(new cwsl_rx);
+    rx->device = device;
+    rx->fs = sample_rate;
+    rx->iq_len = iq_len;
+    rx->geo = geo;
+    rx->sub = iq_len / geo.block_size;
+    rx->ring_seconds = ring_seconds;
+    if (cudaStreamCreateWithFlags(&rx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(CWSL_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return rx.release();
+}
+
+void cwsl_rx_destroy(cwsl_rx_t* rx) {
+    if (!rx) return;
+    DeviceGuard dg(rx->device);
+    if (rx->stream) cudaStreamSynchronize(rx->stream);
+    for (Group& g : rx->groups) free_group_device(g);
+    cudaFree(rx->d_ring);
+    for (auto& pr : rx->ev_demod) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    for (auto& pr : rx->ev_quant) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    for (auto e : rx->ev_pool) cudaEventDestroy(e);
+    if (rx->stream) cudaStreamDestroy(rx->stream);
+    delete rx;
+}
+
+int cwsl_rx_set_mode(cwsl_rx_t* rx, int mode) {
+    if (!rx || (mode != CWSL_MODE_EXACT && mode != CWSL_MODE_FAST)) return fail(CWSL_ERR_INVALID, "bad mode %d", mode);
+    rx->mode = mode;
+    return CWSL_OK;
+}
+
+int cwsl_rx_enable_timing(cwsl_rx_t* rx, int on) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    rx->timing = on != 0;
+    return CWSL_OK;
+}
+
+int cwsl_rx_add_group(cwsl_rx_t* rx, double period_s) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    if (rx->committed) return fail(CWSL_ERR_STATE, "groups must be added before the first push");
+    if (!(period_s > 0) || period_s > 86400) return fail(CWSL_ERR_INVALID, "bad period %g", period_s);
+    Group g;
+    g.period = period_s;
+    g.af_size = cwsl_af_size(period_s);
+    if (g.af_size <= (size_t)rx->iq_len + 1)
+        return fail(CWSL_ERR_INVALID, "period %g s too short for iq_len %u", period_s, rx->iq_len);
+    rx->groups.push_back(std::move(g));
+    return (int)rx->groups.size() - 1;
+}
+
+int cwsl_rx_add_channel(cwsl_rx_t* rx, int group, int32_t demod_freq_hz, int is_usb, float scale) {
+    Group* g = get_group(rx, group);
+    if (!g) return CWSL_ERR_INVALID;
+    if (rx->committed) return fail(CWSL_ERR_STATE, "channels must be added before the first push");
+    if (!(scale > 0.0f) || scale > 1.0f)  // source/CWSL_DIGI.cpp:952-978
+        return fail(CWSL_ERR_INVALID, "audio scale factor %g outside (0, 1]", (double)scale);
+    ChannelHost ch;
+    ch.demod_freq = demod_freq_hz;
+    ch.usb = is_usb != 0;
+    ch.scale = scale;
+    if (!cwsl::nco_tables(rx->geo, demod_freq_hz, is_usb != 0, &ch.nco))
+        return fail(CWSL_ERR_INVALID, "Signal outside of band (demod %d Hz at Fs %u)", demod_freq_hz, rx->fs);
+    g->ch.push_back(std::move(ch));
+    return (int)g->ch.size() - 1;
+}
+
+int cwsl_rx_num_groups(const cwsl_rx_t* rx) { return rx ? (int)rx->groups.size() : CWSL_ERR_INVALID; }
+
+int cwsl_rx_num_channels(const cwsl_rx_t* rx, int group) {
+    if (!rx || group < 0 || group >= (int)rx->groups.size()) return CWSL_ERR_INVALID;
+    return (int)rx->groups[group].ch.size();
+}
+
+size_t cwsl_rx_group_af_size(const cwsl_rx_t* rx, int group) {
+    if (!rx || group < 0 || group >= (int)rx->groups.size()) return 0;
+    return rx->groups[group].af_size;
+}
+
+int cwsl_rx_push_iq(cwsl_rx_t* rx, const float* iq, size_t n_blocks) {
+    return push_common(rx, iq, n_blocks, cudaMemcpyHostToDevice);
+}
+
+int cwsl_rx_push_iq_device(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks) {
+    return push_common(rx, d_iq, n_blocks, cudaMemcpyDeviceToDevice);
+}
+
+int cwsl_rx_bind_device_iq(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks) {
+    if (!rx || !d_iq || n_blocks == 0) return fail(CWSL_ERR_INVALID, "bad arguments");
+    if ((reinterpret_cast<uintptr_t>(d_iq) & 15u) != 0) return fail(CWSL_ERR_INVALID, "IQ buffer must be 16-byte aligned");
+    DeviceGuard dg(rx->device);
+    if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
+    const bool was_bound = rx->bound;
+    rx->bound = true;
+    int rc = commit(rx);
+    if (rc != CWSL_OK) {
+        rx->bound = was_bound;
+        return rc;
+    }
+    const uint64_t blocks = (uint64_t)n_blocks * rx->sub;
+    if (blocks > 0xFFFFFFF0ull) return fail(CWSL_ERR_INVALID, "slot too long");
+    rx->ring_ptr = reinterpret_cast<const float2*>(d_iq);
+    rx->ring_blocks = (uint32_t)blocks;
+    rx->abs_written = blocks;
+    for (Group& g : rx->groups) {
+        g.slot_start = 0;
+        g.processed = 0;
+        g.iq_blocks = n_blocks;
+    }
+    return CWSL_OK;
+}
+
+int cwsl_rx_process(cwsl_rx_t* rx, int group) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    DeviceGuard dg(rx->device);
+    if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
+    int rc = commit(rx);
+    if (rc != CWSL_OK) return rc;
+    if (group >= 0) {
+        Group* g = get_group(rx, group);
+        return g ? process_group(rx, *g) : CWSL_ERR_INVALID;
+    }
+    for (Group& g : rx->groups)
+        if ((rc = process_group(rx, g)) != CWSL_OK) return rc;
+    return CWSL_OK;
+}
+
+int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_index) {
+    Group* g = get_group(rx, group);
+    if (!g) return CWSL_ERR_INVALID;
+    DeviceGuard dg(rx->device);
+    if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
+    int rc = commit(rx);
+    if (rc != CWSL_OK) return rc;
+    if ((rc = process_group(rx, *g)) != CWSL_OK) return rc;
+    const uint32_t C = (uint32_t)g->ch.size();
+    cwsl::QuantLaunch q;
+    q.audio = g->d_audio;
+    q.af_stride = g->af_stride;
+    q.n_channels = C;
+    q.write_index = (uint32_t)g->processed;
+    q.af_size = (uint32_t)g->af_size;
+    q.maxbits = g->d_maxbits;
+    q.scale = g->d_scale;
+    q.out = g->d_out;
+    q.factor_out = g->d_factor;
+    q.max_out = g->d_maxval;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (rx->timing) {
+        e0 = get_event(rx);
+        e1 = get_event(rx);
+        CK(cudaEventRecord(e0, rx->stream));
+    }
+    CK(cwsl::launch_quantise(q, rx->stream));
+    CK(cwsl::launch_clear_u32(g->d_maxbits, C, rx->stream));  // next slot starts from max|x| = 0
+    if (rx->timing) {
+        CK(cudaEventRecord(e1, rx->stream));
+        rx->ev_quant.emplace_back(e0, e1);
+    }
+    if (out_i16)
+        CK(cudaMemcpyAsync(out_i16, g->d_out, (size_t)C * g->af_size * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                           rx->stream));
+    if (write_index) *write_index = (size_t)g->processed;
+    g->last_write_index = (size_t)g->processed;
+    g->have_result = true;
+    // slot reset: fresh SSBD per slot (source/Instance.cpp:251)
+    g->slot_start = rx->abs_written;
+    g->processed = 0;
+    g->iq_blocks = 0;
+    return CWSL_OK;
+}
+
+const int16_t* cwsl_rx_device_audio(const cwsl_rx_t* rx, int group) {
+    if (!rx || group < 0 || group >= (int)rx->groups.size()) return nullptr;
+    return rx->groups[group].d_out;
+}
+
+int cwsl_rx_read_float_audio(cwsl_rx_t* rx, int group, int channel, float* out) {
+    Group* g = get_group(rx, group);
+    if (!g || !out) return CWSL_ERR_INVALID;
+    if (!g->have_result || g->processed != 0) return fail(CWSL_ERR_STATE, "no finished slot available");
+    if (channel < 0 || channel >= (int)g->ch.size()) return fail(CWSL_ERR_INVALID, "bad channel %d", channel);
+    DeviceGuard dg(rx->device);
+    CK(cudaStreamSynchronize(rx->stream));
+    std::memset(out, 0, g->af_size * sizeof(float));
+    CK(cudaMemcpy(out, g->d_audio + (size_t)channel * g->af_stride, g->last_write_index * sizeof(float),
+                  cudaMemcpyDeviceToHost));
+    return CWSL_OK;
+}
+
+int cwsl_rx_channel_stats(cwsl_rx_t* rx, int group, int channel, float* max_val, float* factor) {
+    Group* g = get_group(rx, group);
+    if (!g) return CWSL_ERR_INVALID;
+    if (!g->have_result || g->processed != 0) return fail(CWSL_ERR_STATE, "no finished slot available");
+    if (channel < 0 || channel >= (int)g->ch.size()) return fail(CWSL_ERR_INVALID, "bad channel %d", channel);
+    DeviceGuard dg(rx->device);
+    CK(cudaStreamSynchronize(rx->stream));
+    if (max_val) CK(cudaMemcpy(max_val, g->d_maxval + channel, sizeof(float), cudaMemcpyDeviceToHost));
+    if (factor) CK(cudaMemcpy(factor, g->d_factor + channel, sizeof(float), cudaMemcpyDeviceToHost));
+    return CWSL_OK;
+}
+
+int cwsl_rx_synchronize(cwsl_rx_t* rx) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    DeviceGuard dg(rx->device);
+    CK(cudaStreamSynchronize(rx->stream));
+    return CWSL_OK;
+}
+
+void* cwsl_rx_stream(cwsl_rx_t* rx) { return rx ? (void*)rx->stream : nullptr; }
+
+int cwsl_rx_kernel_times(cwsl_rx_t* rx, float* demod_ms, float* quant_ms, int* demod_launches, int* quant_launches) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    DeviceGuard dg(rx->device);
+    CK(cudaStreamSynchronize(rx->stream));
+    float dsum = 0, qsum = 0;
+    for (auto& pr : rx->ev_demod) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        dsum += ms;
+        rx->ev_pool.push_back(pr.first);
+        rx->ev_pool.push_back(pr.second);
+    }
+    for (auto& pr : rx->ev_quant) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        qsum += ms;
+        rx->ev_pool.push_back(pr.first);
+        rx->ev_pool.push_back(pr.second);
+    }
+    if (demod_ms) *demod_ms = dsum;
+    if (quant_ms) *quant_ms = qsum;
+    if (demod_launches) *demod_launches = (int)rx->ev_demod.size();
+    if (quant_launches) *quant_launches = (int)rx->ev_quant.size();
+    rx->ev_demod.clear();
+    rx->ev_quant.clear();
+    return CWSL_OK;
+}
+
+int cwsl_measure_fp32_peak(int device, float* ffma_tflops, float* ffma2_tflops) {
+    int n = cwsl_device_count();
+    if (n <= 0) return fail(CWSL_ERR_CUDA, "no CUDA device available");
+    if (device < 0 || device >= n) return fail(CWSL_ERR_INVALID, "device %d out of range", device);
+    DeviceGuard dg(device);
+    CK(cwsl::measure_fp32_peak(ffma_tflops, ffma2_tflops));
+    return CWSL_OK;
+}
+
+}  // extern "C"

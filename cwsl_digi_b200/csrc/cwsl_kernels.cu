@@ -1,0 +1,563 @@
+// sm_100a kernels of the CWSL_DIGI receive front-end: NCO mix -> LowPass FIR -> decimate ->
+// Weaver SSB demod (source/SSBD.hpp:128-183) and normalise -> int16 (source/Instance.cpp:238-241,
+// :294-338), batched over every decoder channel of a receiver.
+//
+// Math. For channel c, SSBD block k = BS input samples:
+//   S[k][n]  = sum_{m<BS} (x[BS*k+m] * tone_c[m]) * h[BS*n+m]            n = 0..31
+//   y_c[b]   = sum_{n=0..31, k=b-31+n>=0} S[k][n] * P_c[k]               (ascending n)
+//   audio[b] = {+Re, -Im*sign, -Re, +Im*sign}[b & 3] of y_c[b]
+// P_c[k] = phase_inc_c^k by the reference's float recurrence (phase table, built once per channel).
+//
+// Two kernels:
+//   demod_exact_kernel : one thread per output, every float op unfused in the reference's order
+//                        -> bit-identical to oracle/_ref.
+//   demod_fast_kernel  : one thread per R consecutive blocks; the IQ rows are staged into shared
+//                        memory by the TMA bulk-copy engine (cp.async.bulk + mbarrier) once per CTA
+//                        and re-used by all channels the CTA walks; mix and FIR are packed
+//                        fma.rn.f32x2 (FFMA2) with the real tap broadcast from a uniform register
+//                        (constant bank), so the 512-MAC inner product has no load at all; partial
+//                        sums are exchanged through shared memory; Weaver select, max|x| and the
+//                        float audio store are fused in the epilogue.
+#include "cwsl_kernels.hpp"
+
+#include <cstdio>
+
+namespace cwsl {
+
+// ------------------------------------------------------------------------------------------
+// Constant-bank taps. natural: h[BS*n+m]; transposed: ht[m*32+n] (what the fast kernel walks).
+// One pair per supported block size (Fs = 12000*BS), so receivers of different rates coexist.
+// ------------------------------------------------------------------------------------------
+__constant__ float c_h16[512];
+__constant__ float c_ht16[512];
+__constant__ float c_h8[256];
+__constant__ float c_ht8[256];
+__constant__ float c_h4[128];
+__constant__ float c_ht4[128];
+
+template <int BS>
+__device__ __forceinline__ float tap_nat(int i) {
+    if constexpr (BS == 16) return c_h16[i];
+    else if constexpr (BS == 8) return c_h8[i];
+    else return c_h4[i];
+}
+template <int BS>
+__device__ __forceinline__ float tap_tr(int i) {
+    if constexpr (BS == 16) return c_ht16[i];
+    else if constexpr (BS == 8) return c_ht8[i];
+    else return c_ht4[i];
+}
+
+cudaError_t upload_taps(uint32_t block_size, const float* taps) {
+    const uint32_t n = 32 * block_size;
+    float tr[512];
+    for (uint32_t m = 0; m < block_size; ++m)
+        for (uint32_t k = 0; k < 32; ++k) tr[m * 32 + k] = taps[block_size * k + m];
+    cudaError_t e;
+    switch (block_size) {
+        case 16:
+            if ((e = cudaMemcpyToSymbol(c_h16, taps, n * sizeof(float))) != cudaSuccess) return e;
+            return cudaMemcpyToSymbol(c_ht16, tr, n * sizeof(float));
+        case 8:
+            if ((e = cudaMemcpyToSymbol(c_h8, taps, n * sizeof(float))) != cudaSuccess) return e;
+            return cudaMemcpyToSymbol(c_ht8, tr, n * sizeof(float));
+        case 4:
+            if ((e = cudaMemcpyToSymbol(c_h4, taps, n * sizeof(float))) != cudaSuccess) return e;
+            return cudaMemcpyToSymbol(c_ht4, tr, n * sizeof(float));
+        default:
+            return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long as_u64(float2 v) {
+    return *reinterpret_cast<unsigned long long*>(&v);
+}
+__device__ __forceinline__ float2 as_f2(unsigned long long v) { return *reinterpret_cast<float2*>(&v); }
+
+// packed 2 x fp32 (Blackwell FFMA2/FMUL2/FADD2): one issue slot, two lanes of the FMA pipe
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(as_u64(a)), "l"(as_u64(b)), "l"(as_u64(c)));
+    return as_f2(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return as_f2(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return as_f2(d);
+}
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }  // scalar broadcast operand
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+// TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void atomic_max_abs(unsigned* addr, float warp_local_max) {
+    const unsigned bits = __float_as_uint(warp_local_max);  // non-negative floats order like uints
+    const unsigned m = __reduce_max_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(addr, m);
+}
+
+// Compile-time copy of the taps with the FIR row update unrolled around them (FFMA2 immediates).
+template <int BS>
+struct FirRow;
+#include "cwsl_taps_baked.inc"
+
+const float* baked_taps_transposed(uint32_t block_size) {
+    switch (block_size) {
+        case 16: return kTapsT16;
+        case 8: return kTapsT8;
+        case 4: return kTapsT4;
+        default: return nullptr;
+    }
+}
+
+// Weaver select of SSBD::Iterate (source/SSBD.hpp:132-135); sign flips are exact.
+__device__ __forceinline__ float weaver(float re, float im, uint32_t b, float sign) {
+    switch (b & 3u) {
+        case 0: return re;
+        case 1: return __fmul_rn(-im, sign);
+        case 2: return -re;
+        default: return __fmul_rn(im, sign);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase tables: P[k] = phase_inc^k, the float recurrence of source/SSBD.hpp:174 with
+// libstdc++'s complex multiply (ac-bd, ad+bc), each operation rounded separately (no FMA).
+// Sequential per table by construction (a parallel scan would change the rounding).
+// ------------------------------------------------------------------------------------------
+__global__ void phase_table_kernel(const float2* __restrict__ inc, float2* const* __restrict__ tables, uint32_t n,
+                                   uint32_t length) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float ir = inc[i].x, ii = inc[i].y;
+    float2* __restrict__ out = tables[i];
+    float pr = 1.0f, pi = 0.0f;
+    for (uint32_t k = 0; k < length; ++k) {
+        out[k] = make_float2(pr, pi);
+        const float a = __fmul_rn(pr, ir), b = __fmul_rn(pi, ii);
+        const float c = __fmul_rn(pr, ii), d = __fmul_rn(pi, ir);
+        pr = __fsub_rn(a, b);
+        pi = __fadd_rn(c, d);
+    }
+}
+
+cudaError_t launch_phase_tables(const float2* phase_inc, float2* const* tables, uint32_t n, uint32_t length,
+                                cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    phase_table_kernel<<<(n + 31) / 32, 32, 0, s>>>(phase_inc, tables, n, length);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// EXACT demodulator: gather form, one thread per (channel, output sample); unfused float ops in
+// the reference's order (source/SSBD.hpp:164-181) -> bit-identical to the reference chain.
+// ------------------------------------------------------------------------------------------
+template <int BS>
+__global__ void __launch_bounds__(128) demod_exact_kernel(DemodLaunch p) {
+    const uint32_t c = blockIdx.y;
+    const uint32_t b = p.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float2 s_tone[BS];
+    if (threadIdx.x < BS) s_tone[threadIdx.x] = p.tone[(size_t)c * BS + threadIdx.x];
+    __syncthreads();
+    float out = 0.0f;
+    const bool live = b < p.b1;
+    if (live) {
+        const float2* __restrict__ P = p.phase[c];
+        float wr = 0.0f, wi = 0.0f;
+#pragma unroll 1
+        for (int n = 0; n < 32; ++n) {
+            const int64_t k = (int64_t)b - 31 + n;
+            if (k < 0) continue;  // fresh SSBD: zero history (source/Instance.cpp:251)
+            const uint32_t row = (uint32_t)((p.ring_off + (uint64_t)k) % p.ring_blocks);
+            const float4* __restrict__ x = reinterpret_cast<const float4*>(p.iq_ring + (size_t)row * BS);
+            float sr = 0.0f, si = 0.0f;
+#pragma unroll
+            for (int m2 = 0; m2 < BS / 2; ++m2) {
+                const float4 xx = __ldg(x + m2);
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int m = 2 * m2 + s;
+                    const float xr = s ? xx.z : xx.x, xi = s ? xx.w : xx.y;
+                    const float tr = s_tone[m].x, ti = s_tone[m].y;
+                    const float vr = __fsub_rn(__fmul_rn(xr, tr), __fmul_rn(xi, ti));  // in[m]*tone[m]
+                    const float vi = __fadd_rn(__fmul_rn(xr, ti), __fmul_rn(xi, tr));
+                    const float h = tap_nat<BS>(n * BS + m);
+                    sr = __fadd_rn(sr, __fmul_rn(vr, h));  // sum += (..)*filter[m+n*BlockSize]
+                    si = __fadd_rn(si, __fmul_rn(vi, h));
+                }
+            }
+            const float2 ph = P[k];
+            wr = __fadd_rn(wr, __fsub_rn(__fmul_rn(sr, ph.x), __fmul_rn(si, ph.y)));  // workspace += sum*phase
+            wi = __fadd_rn(wi, __fadd_rn(__fmul_rn(sr, ph.y), __fmul_rn(si, ph.x)));
+        }
+        out = weaver(wr, wi, b, p.sign[c]);
+        p.audio[(size_t)c * p.af_stride + b] = out;
+    }
+    atomic_max_abs(p.maxbits + c, live ? fabsf(out) : 0.0f);
+}
+
+cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
+    if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
+    dim3 grid((p.b1 - p.b0 + 127) / 128, p.n_channels);
+    switch (p.block_size) {
+        case 16: demod_exact_kernel<16><<<grid, 128, 0, s>>>(p); break;
+        case 8: demod_exact_kernel<8><<<grid, 128, 0, s>>>(p); break;
+        case 4: demod_exact_kernel<4><<<grid, 128, 0, s>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// FAST demodulator.
+//
+// CTA = NT threads; thread t owns R consecutive SSBD blocks kbase = kt0 + t*R .. +R-1 ("row").
+// Rows are brought into shared memory by per-row TMA bulk copies (row stride padded by 16 B so
+// the per-thread LDS.128 of "my row" are bank-conflict free) and stay there while the CTA walks
+// its channels. Per channel every thread:
+//   mixes its R blocks with w[m] = tone_c[m]*P_c[k] (packed complex multiply),
+//   accumulates acc[r+31-n] += v[m]*h[16n+m] for all 32 tap rows (FFMA2, tap = uniform-register
+//   broadcast) -> 31+R partial sums indexed by output offset,
+//   hands acc[R..30+R] to the R-aligned later threads through shared memory and finishes its own
+//   R outputs acc[0..R-1] with what the earlier threads handed over.
+// Tiles overlap by 32 blocks (the first 32/R threads only produce hand-over data), so every
+// (tile, channel group) CTA is independent.
+// ------------------------------------------------------------------------------------------
+constexpr int kFastGMax = 32;  // channels walked per CTA (tone tables staged in smem)
+
+template <int BS, int R, int NT>
+struct FastCfg {
+    static constexpr int kRowBytes = R * BS * 8;
+    static constexpr int kRowStride = kRowBytes + 16;
+    static constexpr int kHaloT = 32 / R;
+    static constexpr int kTileOut = (NT - kHaloT) * R;
+    static constexpr int kNE = 31;
+    static constexpr size_t kXBytes = (size_t)NT * kRowStride;
+    static constexpr size_t kEBytes = (size_t)NT * kNE * 8;
+    static constexpr size_t kOBytes = (size_t)NT * R * 8;
+    static constexpr size_t kToneBytes = (size_t)kFastGMax * BS * 8;
+    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + 16;
+};
+
+template <int BS, int R, int NT>
+__global__ void __launch_bounds__(NT, 2) demod_fast_kernel(DemodLaunch p, uint32_t ch_per_cta) {
+    using Cfg = FastCfg<BS, R, NT>;
+    static_assert(32 % R == 0 && (R == 2 || R == 4), "R must be 2 or 4");
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* xs = smem;
+    float2* E = reinterpret_cast<float2*>(smem + Cfg::kXBytes);
+    float2* O = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kEBytes);
+    float4* tone_s = reinterpret_cast<float4*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes);
+
+    const int t = threadIdx.x;
+    const int64_t kt0 = (int64_t)p.b0 + (int64_t)blockIdx.x * Cfg::kTileOut - 32;
+    const int64_t kbase = kt0 + (int64_t)t * R;
+    const bool row_valid = kbase >= 0 && kbase + R <= (int64_t)p.b1;
+    const uint32_t c0 = blockIdx.y * ch_per_cta;
+    const uint32_t nch = min(ch_per_cta, p.n_channels - c0);
+
+    // ---- stage this tile's IQ rows (TMA bulk copies, one per thread row) ----
+    const uint32_t bar_a = smem_u32(bar);
+    if (t == 0) {
+        mbar_init(bar_a, 1);
+        fence_mbar_init();
+        int64_t lo = kt0 >= 0 ? 0 : (-kt0 + R - 1) / R;
+        int64_t hi = ((int64_t)p.b1 - kt0) / R;
+        if (hi > NT) hi = NT;
+        const uint32_t rows = hi > lo ? (uint32_t)(hi - lo) : 0u;
+        mbar_arrive_expect_tx(bar_a, rows * Cfg::kRowBytes);
+    }
+    __syncthreads();
+    if (row_valid) {
+        const uint32_t row = (uint32_t)((p.ring_off + (uint64_t)kbase) % p.ring_blocks);
+        tma_bulk_g2s(smem_u32(xs + (size_t)t * Cfg::kRowStride), p.iq_ring + (size_t)row * BS, Cfg::kRowBytes, bar_a);
+    }
+    for (uint32_t i = t; i < nch * (BS / 2); i += NT)
+        tone_s[i] = reinterpret_cast<const float4*>(p.tone)[(size_t)c0 * (BS / 2) + i];
+    __syncthreads();
+    mbar_wait(bar_a, 0);
+
+    const float4* __restrict__ xrow = reinterpret_cast<const float4*>(xs + (size_t)t * Cfg::kRowStride);
+    float2* __restrict__ Et = E + (size_t)t * Cfg::kNE;
+    float2* __restrict__ Ot = O + (size_t)t * R;
+
+    for (uint32_t ci = 0; ci < nch; ++ci) {
+        const uint32_t c = c0 + ci;
+        // acc[i] = partial sum for output offset (blocks done so far) + i
+        float2 acc[32];
+#pragma unroll
+        for (int o = 0; o < 32; ++o) acc[o] = make_float2(0.0f, 0.0f);
+
+        if (row_valid) {
+            const float2* __restrict__ pp = p.phase[c] + kbase;
+            const float4* __restrict__ tn = tone_s + (size_t)ci * (BS / 2);
+#pragma unroll 1
+            for (int r = 0; r < R; ++r) {
+                const float2 Pk = __ldg(pp + r);
+#pragma unroll
+                for (int m2 = 0; m2 < BS / 2; ++m2) {
+                    const float4 xx = xrow[r * (BS / 2) + m2];  // two IQ samples
+                    const float4 tt = tn[m2];                  // their two tone entries
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const int m = 2 * m2 + s;
+                        // mix: v = x[m] * (tone[m] * P[k]); (a+ib)(c+id) = a*(c,d) + b*(-d,c)
+                        const float2 tn_m = s ? make_float2(tt.z, tt.w) : make_float2(tt.x, tt.y);
+                        float2 w = fmul2(tn_m, bc(Pk.x));
+                        w = ffma2(make_float2(-tn_m.y, tn_m.x), bc(Pk.y), w);
+                        const float xr = s ? xx.z : xx.x, xi = s ? xx.w : xx.y;
+                        float2 v = fmul2(w, bc(xr));
+                        v = ffma2(make_float2(-w.y, w.x), bc(xi), v);
+                        // FIR: tap row n of this block feeds output offset 31-n
+                        FirRow<BS>::apply(m, v, acc);
+                    }
+                }
+                // offset 0 is complete as far as this thread is concerned; slide the window
+                Ot[r] = acc[0];
+#pragma unroll
+                for (int o = 0; o < 31; ++o) acc[o] = acc[o + 1];
+                acc[31] = make_float2(0.0f, 0.0f);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) Ot[r] = make_float2(0.0f, 0.0f);
+        }
+
+        // ---- exchange partial sums: acc[0..30] are offsets R..R+30 ----
+#pragma unroll
+        for (int o = 0; o < 31; ++o) Et[o] = acc[o];
+        __syncthreads();
+        float2 own[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) own[j] = Ot[j];
+#pragma unroll
+        for (int i = 1; i * R <= 30 + R; ++i) {
+            if (t - i >= 0) {
+                const float2* __restrict__ Ei = E + (size_t)(t - i) * Cfg::kNE;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int o = j + i * R;
+                    if (o <= 30 + R) own[j] = fadd2(own[j], Ei[o - R]);
+                }
+            }
+        }
+
+        // ---- epilogue: Weaver select, float audio store, max|x| ----
+        float lmax = 0.0f;
+        if (row_valid && t >= Cfg::kHaloT && kbase >= (int64_t)p.b0) {
+            const float sign = p.sign[c];
+            float o4[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                o4[j] = weaver(own[j].x, own[j].y, (uint32_t)(kbase + j), sign);
+                lmax = fmaxf(lmax, fabsf(o4[j]));
+            }
+            float* dst = p.audio + (size_t)c * p.af_stride + kbase;
+            if constexpr (R == 4)
+                *reinterpret_cast<float4*>(dst) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            else
+                *reinterpret_cast<float2*>(dst) = make_float2(o4[0], o4[1]);
+        }
+        atomic_max_abs(p.maxbits + c, lmax);
+        __syncthreads();  // E/O are rewritten by the next channel
+    }
+}
+
+template <int BS, int R, int NT>
+static cudaError_t launch_fast_t(const DemodLaunch& p, cudaStream_t s) {
+    using Cfg = FastCfg<BS, R, NT>;
+    static bool attr_done = false;
+    auto kern = demod_fast_kernel<BS, R, NT>;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const uint32_t n_out = p.b1 - p.b0;
+    const uint32_t tiles = (n_out + Cfg::kTileOut - 1) / Cfg::kTileOut;
+    uint32_t g = p.n_channels < (uint32_t)kFastGMax ? p.n_channels : (uint32_t)kFastGMax;
+    dim3 grid(tiles, (p.n_channels + g - 1) / g);
+    kern<<<grid, NT, Cfg::kSmem, s>>>(p, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s) {
+    if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
+    switch (p.block_size) {
+        case 16: return launch_fast_t<16, 4, 128>(p, s);
+        case 8: return launch_fast_t<8, 4, 128>(p, s);
+        case 4: return launch_fast_t<4, 4, 128>(p, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// prepareAudio + int16 conversion (source/Instance.cpp:294-338, :238-241), all channels.
+//   factor = 32767/(max+1); factor *= scale; x *= factor; q = (int16)(x + 0.5f)   (trunc toward 0)
+// Each operation is a separately rounded float op, as compiled from the reference with strict
+// IEEE flags. Samples past write_index are the zero tail: (int16)(0*factor + 0.5f) = 0.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quantise_kernel(QuantLaunch p) {
+    const uint32_t c = blockIdx.y;
+    const float maxv = __uint_as_float(p.maxbits[c]);
+    float factor = __fdiv_rn(32767.0f, __fadd_rn(maxv, 1.0f));
+    factor = __fmul_rn(factor, p.scale[c]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (p.factor_out) p.factor_out[c] = factor;
+        if (p.max_out) p.max_out[c] = maxv;
+    }
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8u;
+    if (i0 >= p.af_size) return;
+    const float* __restrict__ src = p.audio + (size_t)c * p.af_stride;
+    int16_t* __restrict__ dst = p.out + (size_t)c * p.af_size;
+    const bool vec = (p.af_size % 8u == 0) && (p.af_stride % 4u == 0);
+    short q[8];
+    if (vec && i0 + 8 <= p.write_index) {
+        const float4 a = *reinterpret_cast<const float4*>(src + i0);
+        const float4 b = *reinterpret_cast<const float4*>(src + i0 + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) q[e] = (short)__float2int_rz(__fadd_rn(__fmul_rn(v[e], factor), 0.5f));
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t i = i0 + e;
+            const float v = (i < p.write_index) ? src[i] : 0.0f;
+            q[e] = (short)__float2int_rz(__fadd_rn(__fmul_rn(v, factor), 0.5f));
+        }
+    }
+    if (vec) {
+        int4 pk;
+        pk.x = (int)((unsigned short)q[0] | ((unsigned)(unsigned short)q[1] << 16));
+        pk.y = (int)((unsigned short)q[2] | ((unsigned)(unsigned short)q[3] << 16));
+        pk.z = (int)((unsigned short)q[4] | ((unsigned)(unsigned short)q[5] << 16));
+        pk.w = (int)((unsigned short)q[6] | ((unsigned)(unsigned short)q[7] << 16));
+        *reinterpret_cast<int4*>(dst + i0) = pk;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (i0 + e < p.af_size) dst[i0 + e] = q[e];
+    }
+}
+
+cudaError_t launch_quantise(const QuantLaunch& p, cudaStream_t s) {
+    if (p.n_channels == 0 || p.af_size == 0) return cudaSuccess;
+    dim3 grid((p.af_size + 2047) / 2048, p.n_channels);
+    quantise_kernel<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+__global__ void clear_u32_kernel(unsigned* p, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0u;
+}
+cudaError_t launch_clear_u32(unsigned* p, uint32_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    clear_u32_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 pipe microbenchmark: register-resident FMA chains, no memory traffic.
+// ------------------------------------------------------------------------------------------
+template <bool PACKED>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, float a, float b, int iters) {
+    float2 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+    const float2 va = make_float2(a, a * 0.999f), vb = make_float2(b, b * 1.001f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (PACKED) {
+                    acc[i] = ffma2(acc[i], va, vb);
+                } else {
+                    acc[i].x = fmaf(acc[i].x, va.x, vb.x);
+                    acc[i].y = fmaf(acc[i].y, va.y, vb.y);
+                }
+            }
+        }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sum += acc[i].x + acc[i].y;
+    if (sum == 12345.678f) out[0] = sum;  // never true; keeps the chains alive
+}
+
+cudaError_t measure_fp32_peak(float* ffma_tflops, float* ffma2_tflops) {
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    float* d = nullptr;
+    if ((e = cudaMalloc(&d, 4)) != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    const double flop = (double)blocks * threads * iters * 4 * 16 * 2 * 2;
+    float best[2] = {0, 0};
+    for (int variant = 0; variant < 2; ++variant) {
+        for (int rep = 0; rep < 6; ++rep) {
+            cudaEventRecord(e0);
+            if (variant == 0)
+                fp32_peak_kernel<false><<<blocks, threads>>>(d, 0.9999f, 1e-4f, iters);
+            else
+                fp32_peak_kernel<true><<<blocks, threads>>>(d, 0.9999f, 1e-4f, iters);
+            cudaEventRecord(e1);
+            if ((e = cudaEventSynchronize(e1)) != cudaSuccess) goto done;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+            if (rep > 0 && tf > best[variant]) best[variant] = tf;
+        }
+    }
+    if (ffma_tflops) *ffma_tflops = best[0];
+    if (ffma2_tflops) *ffma2_tflops = best[1];
+done:
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return e;
+}
+
+}  // namespace cwsl

@@ -1,0 +1,107 @@
+// Host-side table builder of the B200 front-end.
+//
+// The demodulator kernels consume exactly the tables the reference's SSBD<float> object holds,
+// so they are produced here on the host by the same libm calls and the same expression shapes
+// (rounding points) as the reference:
+//   low-pass prototype   source/LowPass.hpp:16-35   (double math, one rounding to float per tap)
+//   DC normalisation     source/SSBD.hpp:66-68      (sequential float sum, float divide)
+//   NCO tone / phase_inc source/SSBD.hpp:110-114    (float phase_delta, glibc cexpf)
+// tests/test_tables.py pins them bit-for-bit against oracle/_ref (the reference's own headers).
+#pragma once
+
+#include <cmath>
+#include <complex>
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+namespace cwsl {
+
+constexpr uint32_t kWaveSR = 12000;   // Wave_SR, source/CWSL_DIGI.hpp:51
+constexpr uint32_t kSSBBW = 6000;     // SSB_BW,  source/CWSL_DIGI.hpp:52
+constexpr uint32_t kLatencyLog2 = 3;  // SSBD ctor default, source/SSBD.hpp:49
+constexpr uint32_t kNumWS = 32;       // FiltOrder/BlockSize = 4*latency for every legal Fs
+constexpr double kPi = 3.14159265358979323846;  // source/LowPass.hpp:13
+
+struct SsbdGeometry {
+    uint32_t fs = 0;
+    uint32_t filt_order = 0;  // latency*2*Fs/B   source/SSBD.hpp:62
+    uint32_t block_size = 0;  // Fs/B/2           source/SSBD.hpp:71
+    uint32_t num_ws = 0;      // FiltOrder/BlockSize
+    uint32_t in_size = 0;     // 2*Fs/B           source/SSBD.hpp:144
+    uint32_t dec_ratio = 0;   // Fs/Wave_SR       source/Instance.cpp:192
+};
+
+// false where the SSBD ctor throws (source/SSBD.hpp:54-59)
+inline bool ssbd_geometry(uint32_t fs, SsbdGeometry* g) {
+    const size_t Fs = fs, B = kSSBBW;
+    if ((Fs / B / 2) * 2 * B != Fs || Fs < 4 * B) return false;
+    const size_t latency = size_t(1) << kLatencyLog2;
+    g->fs = fs;
+    g->filt_order = uint32_t(latency * 2 * Fs / B);
+    g->block_size = uint32_t(Fs / B / 2);
+    g->num_ws = g->filt_order / g->block_size;
+    g->in_size = uint32_t(2 * Fs / B);
+    g->dec_ratio = fs / kWaveSR;
+    return true;
+}
+
+// Hamming-windowed sinc prototype, normalised to unit DC gain.
+inline std::vector<float> lowpass_taps(const SsbdGeometry& g) {
+    const size_t order = g.filt_order;
+    const double bandwidth = kSSBBW / (double)g.fs;
+    std::vector<float> f(order);
+    f[0] = static_cast<float>(0.0);
+    f[order / 2] = static_cast<float>(1.0);
+    const double x0 = -1.0 * order / 2;
+    for (size_t n = 1; n < order / 2; ++n) {
+        const double xPi = (x0 + n) * kPi * bandwidth;
+        const double y = sin(xPi) / xPi * (0.54 - 0.46 * cos(2.0 * kPi * n / (double)order));
+        f[n] = static_cast<float>(y);
+        f[order - n] = static_cast<float>(y);
+    }
+    float sum = 0.0;
+    for (size_t n = 0; n < order; ++n) sum += f[n];
+    for (size_t n = 0; n < order; ++n) f[n] /= sum;
+    return f;
+}
+
+struct NcoTables {
+    std::vector<std::complex<float>> tone;  // [block_size]
+    std::complex<float> phase_inc;
+    float sign = 1.0f;
+};
+
+// false where SSBD::Tune throws (source/SSBD.hpp:100-103)
+inline bool nco_tables(const SsbdGeometry& g, int32_t demod_freq_hz, bool is_usb, NcoTables* t) {
+    const size_t Fs = g.fs, B = kSSBBW;
+    const double F = static_cast<float>(demod_freq_hz);  // source/Instance.cpp:187 passes a float
+    if (fabs(F) > Fs / 2) return false;
+    if (fabs(F + B * (is_usb ? 1.0 : -1.0)) > Fs / 2) return false;
+    const float sign = static_cast<float>(is_usb ? 1.0 : -1.0);
+    const float phase_delta = static_cast<float>(-2.0 * kPi * (F + sign * B / 2.0) / static_cast<double>(Fs));
+    t->sign = sign;
+    t->tone.resize(g.block_size);
+    for (size_t n = 0; n < g.block_size; ++n)
+        t->tone[n] = std::exp(std::complex<float>(0.0, phase_delta * n));
+    t->phase_inc = std::exp(std::complex<float>(0.0, phase_delta * g.block_size));
+    return true;
+}
+
+inline size_t af_size(double period_s) {  // source/Instance.cpp:149
+    return static_cast<size_t>(static_cast<double>(kWaveSR) * static_cast<double>(period_s + 5));
+}
+
+// source/Instance.cpp:268-276 applied to a run of n_iq_blocks blocks starting from an empty buffer
+inline size_t accepted_blocks(size_t n_iq_blocks, uint32_t iq_len, uint32_t dec_ratio, size_t afsize,
+                              size_t write_index = 0) {
+    size_t acc = 0;
+    for (size_t i = 0; i < n_iq_blocks; ++i) {
+        if (write_index + iq_len > afsize - 1) break;  // every later block is dropped as well
+        write_index += iq_len / dec_ratio;
+        ++acc;
+    }
+    return acc;
+}
+
+}  // namespace cwsl

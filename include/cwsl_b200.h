@@ -1,0 +1,172 @@
+/*
+ * cwsl_b200.h -- C ABI of the B200-native CWSL_DIGI receive front-end.
+ *
+ * The reference (alexranaldi/CWSL_DIGI v0.88) has no FFI/plugin seam for this path: the seam is
+ * a set of C++ classes inside one executable. This header is the boundary a maintainer binds
+ * underneath those classes; every entry point names the reference interface it replaces
+ * (paths relative to the reference checkout). INTEGRATION.md shows the reference-side glue.
+ *
+ * Conventions: plain pointers and sizes only; opaque handles; int status (0 = CWSL_OK,
+ * negative = error, text via cwsl_last_error()); the caller owns every host buffer, the library
+ * owns all device memory; calls on one handle are serialised by the caller, different handles
+ * may be driven from different threads / GPUs concurrently. There is no CPU fallback: if no
+ * CUDA device is usable every compute entry point fails with CWSL_ERR_CUDA.
+ */
+#ifndef CWSL_B200_H
+#define CWSL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CWSL_B200_ABI_VERSION 1
+
+#define CWSL_OK 0
+#define CWSL_ERR_INVALID (-1)  /* bad argument; where the reference throws std::invalid_argument
+                                  (source/SSBD.hpp:54-59, :100-103) or rejects a config value */
+#define CWSL_ERR_CUDA (-2)     /* CUDA runtime/driver failure, or no device */
+#define CWSL_ERR_NOMEM (-3)
+#define CWSL_ERR_STATE (-4)    /* call-order error (e.g. push before any channel exists) */
+#define CWSL_ERR_OVERRUN (-5)  /* IQ ring overrun: data needed by an open slot was overwritten
+                                  (the reference logs "ring buffer full", source/Receiver.hpp:222-229) */
+
+/* Arithmetic mode of the demodulator kernels.
+ * EXACT: every float operation of source/SSBD.hpp:160-183 is issued unfused, in the reference's
+ *        order -> float audio and int16 output are bit-identical to the reference chain built
+ *        with strict IEEE flags (oracle/_ref).
+ * FAST:  same tables and the same float phase recurrence, FMA-contracted mix and FIR
+ *        (packed fma.rn.f32x2) -> <= 1 int16 LSB, residual >= 90 dB below signal. */
+#define CWSL_MODE_EXACT 0
+#define CWSL_MODE_FAST 1
+
+typedef struct cwsl_rx cwsl_rx_t;
+
+/* ---- library / device ------------------------------------------------------------------ */
+int cwsl_abi_version(void);
+const char* cwsl_last_error(void); /* thread-local text of the last failure on this thread */
+int cwsl_device_count(void);       /* number of visible CUDA devices, 0 if none */
+
+/* ---- SSBD parameter algebra (host only, no GPU needed) --------------------------------- */
+/* Replaces SSBD<>::GetInRate/GetOutRate/GetInSize/GetOutSize/GetBandwidth/GetDelay
+ * (source/SSBD.hpp:140-154) plus the derived FiltOrder/BlockSize/NumWS (:62,:71,:75).
+ * out[9] = {InRate, OutRate, InSize, OutSize, Bandwidth, Delay, FiltOrder, BlockSize, NumWS}.
+ * CWSL_ERR_INVALID where the SSBD ctor throws (source/SSBD.hpp:54-59). */
+int cwsl_ssbd_params(uint32_t sample_rate, uint32_t out[9]);
+
+/* The tables SSBD<float>(Fs, 6000, float(demod_freq_hz), is_usb) builds in its ctor and Tune()
+ * (source/SSBD.hpp:62-68, :110-114; source/LowPass.hpp:16-35): normalised filter[FiltOrder],
+ * tone[2*BlockSize] (re,im interleaved) and phase_inc[2]. Host only. CWSL_ERR_INVALID for
+ * out-of-band tunings (source/SSBD.hpp:100-103). */
+int cwsl_build_tables(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, float* filter,
+                      float* tone, float* phase_inc);
+
+/* (period + 5 s) * 12000: length of one decoder's audio buffer, source/Instance.cpp:149. */
+size_t cwsl_af_size(double period_s);
+
+/* Number of IQ blocks the demod loop accepts before its "af buffer full" guard drops the rest
+ * (source/Instance.cpp:268-271). */
+size_t cwsl_accepted_blocks(size_t n_iq_blocks, uint32_t iq_len, uint32_t sample_rate, size_t af_size);
+
+/* ---- receiver: one per CWSL shared-memory band (source/Receiver.hpp:52-302) -------------- */
+/* sample_rate / iq_len are SM_HDR.SampleRate / BlockInSamples (source/Receiver.hpp:87-88).
+ * iq_len must be a multiple of SSBD::GetInSize() (the reference silently over-reads otherwise,
+ * source/Instance.cpp:273). ring_seconds sizes the device-resident IQ ring (the reference keeps
+ * ~3 s of blocks on the host, source/Receiver.hpp:132); 0 = size it for the longest slot of the
+ * groups added before the first push. Returns NULL on failure (see cwsl_last_error). */
+cwsl_rx_t* cwsl_rx_create(int device, uint32_t sample_rate, uint32_t iq_len, double ring_seconds);
+void cwsl_rx_destroy(cwsl_rx_t* rx);
+
+/* EXACT or FAST (default FAST). */
+int cwsl_rx_set_mode(cwsl_rx_t* rx, int mode);
+
+/* A slot group = the decoders that share one SyncPredicate, i.e. one mode/period
+ * (source/CWSL_DIGI_Types.hpp:65-145, source/CWSL_DIGI.cpp:134). period_s as getRXPeriod()
+ * (source/CWSL_DIGI.hpp:64-113). Returns the group id (>= 0) or a negative error. */
+int cwsl_rx_add_group(cwsl_rx_t* rx, double period_s);
+
+/* One decoder channel = one Instance + its SSBD<float>(Fs, SSB_BW, float(demod_freq_hz), USB)
+ * (source/Instance.cpp:183-187). demod_freq_hz = int32(calibratedSSBFreq - LO)
+ * (source/Instance.cpp:183); scale = audioScaleFactor_ft or _wspr, 0 < scale <= 1
+ * (source/Instance.cpp:320-329, source/CWSL_DIGI.cpp:952-978). Builds the reference's tables on
+ * the host and the float phase sequence phase_inc^k (source/SSBD.hpp:174) on the device.
+ * Returns the channel index inside the group (>= 0) or a negative error; CWSL_ERR_INVALID for
+ * tunings SSBD::Tune rejects (source/SSBD.hpp:100-103). Must precede the first push. */
+int cwsl_rx_add_channel(cwsl_rx_t* rx, int group, int32_t demod_freq_hz, int is_usb, float scale);
+
+int cwsl_rx_num_groups(const cwsl_rx_t* rx);
+int cwsl_rx_num_channels(const cwsl_rx_t* rx, int group);
+size_t cwsl_rx_group_af_size(const cwsl_rx_t* rx, int group);
+
+/* Append n_blocks IQ blocks (n_blocks * iq_len complex samples, interleaved float32 I,Q as in
+ * source/Receiver.hpp:140) from HOST memory to the receiver's device ring. Replaces
+ * Receiver::readIQ's copy into the ring (source/Receiver.hpp:242-249) AND the N per-decoder
+ * pops of the same block (source/Instance.cpp:260-265): the block crosses PCIe once.
+ * Asynchronous when `iq` is pinned memory. Slots that would lose un-demodulated samples to the
+ * ring wrap are demodulated first. */
+int cwsl_rx_push_iq(cwsl_rx_t* rx, const float* iq, size_t n_blocks);
+
+/* Same, source already in device memory on rx's device (device-to-device copy into the ring). */
+int cwsl_rx_push_iq_device(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks);
+
+/* Zero-copy variant for benchmarks: treat the device buffer d_iq (n_blocks * iq_len samples,
+ * must stay valid until the slot ends) as the complete IQ of the NEXT slot of every group.
+ * Replaces any ring contents; nothing is copied. */
+int cwsl_rx_bind_device_iq(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks);
+
+/* Demodulate everything pushed so far for `group` (or all groups if group < 0) without ending
+ * the slot: the streaming counterpart of the per-block Iterate loop, source/Instance.cpp:273-276.
+ * Asynchronous. */
+int cwsl_rx_process(cwsl_rx_t* rx, int group);
+
+/* Slot edge for `group` = the SyncPredicate firing (source/Instance.cpp:203-253): finishes the
+ * demodulation of the samples pushed since the previous edge, then for EVERY channel of the
+ * group runs prepareAudio (max|x| over the whole buffer, factor = 32767/(max+1)*scale,
+ * source/Instance.cpp:294-338) and the int16 conversion (int16)(x+0.5f)
+ * (source/Instance.cpp:238-241), and resets the group's demodulators (fresh SSBD per slot,
+ * source/Instance.cpp:251). out_i16 is HOST memory [n_channels][af_size] (may be NULL to leave
+ * the result on the device); *write_index receives the number of audio samples demodulated
+ * into each buffer (the rest of af_size is the zero tail). The host copy is asynchronous when
+ * out_i16 is pinned: call cwsl_rx_synchronize() before reading it. */
+int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_index);
+
+/* Device pointer of the last finished slot's int16 audio, [n_channels][af_size]; valid until
+ * the next cwsl_rx_end_slot on the same group. */
+const int16_t* cwsl_rx_device_audio(const cwsl_rx_t* rx, int group);
+
+/* Float audio before normalisation of the last finished slot (what prepareAudio reads,
+ * source/Instance.cpp:295), copied to HOST out[af_size] (zero tail included); synchronous.
+ * Parity/debug aid. */
+int cwsl_rx_read_float_audio(cwsl_rx_t* rx, int group, int channel, float* out);
+
+/* maxVal and final factor prepareAudio computed for the last finished slot
+ * (the values the reference logs, source/Instance.cpp:314,336); synchronous. */
+int cwsl_rx_channel_stats(cwsl_rx_t* rx, int group, int channel, float* max_val, float* factor);
+
+/* Block until all asynchronous work queued on this receiver has finished. */
+int cwsl_rx_synchronize(cwsl_rx_t* rx);
+
+/* The CUDA stream (cudaStream_t) all work of this receiver is queued on, for event timing. */
+void* cwsl_rx_stream(cwsl_rx_t* rx);
+
+/* Record CUDA events around every kernel launch of this receiver (off by default). */
+int cwsl_rx_enable_timing(cwsl_rx_t* rx, int on);
+
+/* Device time (ms, CUDA events on the receiver's stream) of the demodulator kernel launches and
+ * of the normalise+quantise launches queued since the last call; also their launch counts.
+ * Synchronises the stream. Any pointer may be NULL. */
+int cwsl_rx_kernel_times(cwsl_rx_t* rx, float* demod_ms, float* quant_ms, int* demod_launches,
+                         int* quant_launches);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* FP32 FMA-pipe peak of `device`, measured with a register-resident FFMA / packed FFMA2
+ * loop (TFLOP/s, 2 flop per lane-FMA). Used as the roofline denominator of this path, which
+ * is FP32-pipe-bound. */
+int cwsl_measure_fp32_peak(int device, float* ffma_tflops, float* ffma2_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CWSL_B200_H */
