@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- CWSL_DIGI receive front-end on B200: channel-Msamples/s (IQ in x decoders).
+
+Workload (BASELINE.json configs[4], the configuration the metric's per-GPU targets are quoted on):
+  64 synthetic 192 kHz receivers x 1024 decoder channels each, one 15 s FT8 slot per step,
+  demodFreq_c = -96000 + round(c*186000/1023); receivers are partitioned round-robin over the
+  ranks (one process per GPU, no data-path collective) -> "scaling": "strong".
+A step = every receiver of the rank: NCO mix + 512-tap FIR + /16 + SSB demod for all 1024 channels
+(one launch), max|x| -> normalise -> int16 for all channels (one launch), max reset (one launch).
+
+  value   : ch-samples/s with the IQ already resident in HBM (bind_device_iq), all ranks summed
+  e2e     : same metric through the C ABI with HOST buffers: pinned IQ -> cwsl_rx_push_iq (H2D) ->
+            cwsl_rx_end_slot (kernels + D2H of the whole [1024][240000] int16 result)
+  roofline: the demodulator kernel against the FP32 FMA pipe (134 flop per
+            channel-sample; the path is FMA-bound, not HBM-bound); peak = FFMA2 microbenchmark run
+            in this process (MEASURED_PEAKS.json has no FP32 figure); HBM fraction given alongside.
+  cpu_baseline / --impl reference: the reference's own SSBD.hpp/LowPass.hpp chain (oracle/_ref,
+            -O3 -mavx2 -mfma -ffast-math = the shipped /O2 /fp:fast /arch:AVX analogue), one worker
+            thread per host core, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS, IQ_LEN, PERIOD = 192000, 2048, 15.0
+N_RECEIVERS, N_CHANNELS = 64, 1024
+FLOP_PER_CH_SAMPLE = 134.0          # SURVEY.md section 8d (mix 6 + 32 taps x 4)
+METRIC, UNIT = "channel-Msamples/s (IQ in x decoders)", "ch-Msamples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--receivers", type=int, default=N_RECEIVERS, help="total receivers over all ranks")
+    ap.add_argument("--channels", type=int, default=N_CHANNELS)
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-time budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"stress sweep: {a.receivers} synthetic 192 kHz receivers x {a.channels} channels, one 15 s FT8 slot "
+            f"per receiver per step (BASELINE.json configs[4])")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------------
+def host_iq(seed, n_blocks):
+    """Same statistics as the GPU workload: Gaussian sigma=300 per component + a few strong carriers."""
+    rng = np.random.default_rng(seed)
+    n = n_blocks * IQ_LEN
+    x = rng.standard_normal(2 * n, dtype=np.float32) * np.float32(300.0)
+    t = np.arange(n, dtype=np.float64)
+    for j in range(4):
+        f = -90000 + 45000 * j + 1234
+        ph = 2 * np.pi * ((f * t) % FS) / FS
+        x[0::2] += (4000 * np.cos(ph)).astype(np.float32)
+        x[1::2] += (4000 * np.sin(ph)).astype(np.float32)
+    return x
+
+
+def cpu_chain(freqs, n_blocks, budget_s, fast=True, max_reps=50):
+    """Time the reference chain (oracle/_ref) on all host cores. Returns dict for the JSON line."""
+    from oracle.oracle import Ref, af_size
+    kind = "reference"
+    try:
+        ref = Ref(fast=fast)
+    except Exception as e:  # noqa: BLE001  prebuilt oracle/_ref missing: report it, never substitute anything
+        return dict(value=None, unit=UNIT, cores=0, kind=kind, sample=f"oracle/_ref unavailable: {e}")
+    cores = ref.hardware_concurrency() or os.cpu_count() or 1
+    iq = host_iq(7, n_blocks)
+    scales = np.full(len(freqs), 0.9, np.float32)
+    afs = af_size(PERIOD)
+    best, total, reps = None, 0.0, 0
+    while reps < max_reps and (reps < 2 or total < budget_s):
+        sec, _, _ = ref.chain_threads(FS, freqs, scales, iq, IQ_LEN, afs, max_threads=cores)
+        total += sec
+        reps += 1
+        best = sec if best is None else min(best, sec)
+        if sec > budget_s:
+            break
+    chs = float(len(freqs)) * n_blocks * IQ_LEN
+    flags = "-O3 -mavx2 -mfma -ffast-math" if fast else "-O2 -ffp-contract=off (strict IEEE, parity build)"
+    return dict(value=chs / best / 1e6, unit=UNIT, cores=int(cores), kind=kind, seconds=best, reps=reps,
+                sample=f"1 receiver x {len(freqs)} channels (every {N_CHANNELS // max(1, len(freqs))}th of the stress "
+                       f"set) x one 15 s FT8 slot ({n_blocks * IQ_LEN} IQ samples), reference SSBD.hpp chain built "
+                       f"with {flags}, {cores} worker threads, best of {reps}")
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cwsl_digi_b200 import synth
+    cores = os.cpu_count() or 1
+    n_ch = int(min(a.channels, max(32, 4 * cores)))
+    freqs = synth.stress_demod_freqs(a.channels)[:: max(1, a.channels // n_ch)][:n_ch].astype(np.int32)
+    n_blocks = int(PERIOD * FS) // IQ_LEN
+    vals, secs = [], []
+    from oracle.oracle import Ref, af_size
+    ref = Ref(fast=True)
+    cores = ref.hardware_concurrency() or cores
+    iq = host_iq(7, n_blocks)
+    scales = np.full(len(freqs), 0.9, np.float32)
+    afs = af_size(PERIOD)
+    chs = float(len(freqs)) * n_blocks * IQ_LEN
+    for i in range(a.warmup + a.steps):
+        sec, _, _ = ref.chain_threads(FS, freqs, scales, iq, IQ_LEN, afs, max_threads=cores)
+        if i >= a.warmup:
+            secs.append(sec)
+    tot = sum(secs)
+    value = chs * len(secs) / tot / 1e6
+    sample = (f"each step = 1 receiver x {len(freqs)} channels of the stress set x one 15 s FT8 slot; reference "
+              f"SSBD.hpp/LowPass.hpp chain (oracle/_ref, -O3 -mavx2 -mfma -ffast-math), {cores} worker threads")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=1e3 * tot / len(secs), higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=workload_name(a), sample=sample),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=int(cores), kind="reference", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                x_realtime_per_receiver=PERIOD / (tot / len(secs)) if len(freqs) else None, gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    import cwsl_digi_b200 as cw
+    from cwsl_digi_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        a.gpus = world
+    if not torch.cuda.is_available() or cw.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    mode = cw.MODE_FAST if a.mode == "fast" else cw.MODE_EXACT
+    my_rx = list(range(rank, a.receivers, world))          # one receiver/band per GPU, round-robin
+    n_blocks = int(PERIOD * FS) // IQ_LEN                   # 1406 IQ blocks = 2 879 488 samples
+    n_iq = n_blocks * IQ_LEN
+    freqs = synth.stress_demod_freqs(a.channels)
+    afs = cw.af_size(PERIOD)
+
+    # synthetic IQ, one distinct array per receiver (seed 20261017 + receiver id), generated on the device
+    iq_dev = []
+    t = torch.arange(n_iq, device="cuda", dtype=torch.float64)
+    for r in my_rx:
+        g = torch.Generator(device="cuda").manual_seed(synth.BASE_SEED + r)
+        x = torch.randn(2 * n_iq, device="cuda", generator=g) * 300.0
+        for j in range(4):
+            f = -90000 + 45000 * j + 1234 + 17 * r
+            ph = 2 * np.pi * ((f * t) % FS) / FS
+            x[0::2] += (4000 * torch.cos(ph)).float()
+            x[1::2] += (4000 * torch.sin(ph)).float()
+        iq_dev.append(x.contiguous())
+    del t
+
+    stream = torch.cuda.current_stream()
+    rxs = []
+    for _ in my_rx:
+        rx = cw.Receiver(local, FS, IQ_LEN, mode=mode)
+        grp = rx.add_group(PERIOD)
+        for f in freqs:
+            rx.add_channel(grp, int(f), 0.9)
+        rx.set_stream(stream.cuda_stream)
+        rxs.append(rx)
+
+    def step_resident():
+        for rx, x in zip(rxs, iq_dev):
+            rx.bind_device_iq(x.data_ptr(), n_blocks)
+            rx.end_slot(0, None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp32 = cw.measure_fp32_peak(local)
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    for _ in range(max(3, a.warmup)):
+        step_resident()
+    barrier()
+    for rx in rxs:
+        rx.enable_timing(True)
+        rx.kernel_times()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    kt = [rx.kernel_times() for rx in rxs]
+    for rx in rxs:
+        rx.enable_timing(False)
+    demod_ms = sum(k["demod_ms"] for k in kt)
+    quant_ms = sum(k["quant_ms"] for k in kt)
+    demod_launches = sum(k["demod_launches"] for k in kt)
+    launches = sum(k["demod_launches"] + 2 * k["quant_launches"] for k in kt)
+
+    tmax = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / a.steps
+    chs_step_total = float(a.receivers) * a.channels * n_iq
+    value = chs_step_total / (ms_step * 1e-3) / 1e6
+
+    # ---- end-to-end arm: host IQ in, host int16 out, through the C ABI ------------------------------
+    e2e = None
+    if not a.no_e2e:
+        for rx in rxs:
+            rx.synchronize()
+        NBUF = min(4, len(rxs))
+        host_in = [torch.empty(2 * n_iq, dtype=torch.float32).pin_memory() for _ in my_rx]
+        for h, x in zip(host_in, iq_dev):
+            h.copy_(x)
+        host_out = [torch.empty((a.channels, afs), dtype=torch.int16).pin_memory() for _ in range(NBUF)]
+        streams = [torch.cuda.Stream() for _ in range(NBUF)]
+        for i in range(len(my_rx)):
+            rxs[i].set_stream(streams[i % NBUF].cuda_stream)
+        checks = [0]
+
+        def step_e2e():
+            for i, rx in enumerate(rxs):
+                b = i % NBUF
+                if i >= NBUF:
+                    streams[b].synchronize()            # previous user of this pinned buffer has landed
+                    checks[0] ^= int(host_out[b][0, 1000])   # consumer touches the result
+                rx.push_iq((host_in[i].data_ptr(), n_blocks))
+                rx.end_slot(0, host_out[b].data_ptr())
+            for s in streams:
+                s.synchronize()
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream())
+        for _ in range(a.steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        tw = torch.tensor([wall], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall = float(tw.item())
+        e2e = dict(value=chs_step_total * a.steps / wall / 1e6, unit=UNIT,
+                   h2d_bytes_per_step=int(len(my_rx) * n_iq * 8 * world),
+                   d2h_bytes_per_step=int(len(my_rx) * a.channels * afs * 2 * world),
+                   ms_per_step=1e3 * wall / a.steps,
+                   note="pinned host IQ -> cwsl_rx_push_iq -> cwsl_rx_end_slot(host int16); timed region includes "
+                        "every H2D and D2H copy; wall clock around a device synchronize, max over ranks")
+
+    # ---- station-level gather (NCCL): rank 0 collects one channel's audio per rank ------------------------
+    gathered = None
+    if world > 1:
+        sample = torch.empty(afs, dtype=torch.int16, device="cuda")
+        rxs[0].copy_device_audio(0, 0, sample.data_ptr())   # last slot, my first receiver, channel 0
+        rxs[0].synchronize()
+        bucket = [torch.empty_like(sample) for _ in range(world)] if rank == 0 else None
+        dist.gather(sample, bucket, dst=0)
+        if rank == 0:
+            gathered = [int(b.to(torch.int64).abs().sum().item()) for b in bucket]
+
+    if rank == 0:
+        # roofline of the dominant kernel (demod_fast_kernel / demod_exact_kernel)
+        launch_ms = demod_ms / max(1, demod_launches)
+        flop_per_launch = FLOP_PER_CH_SAMPLE * a.channels * n_iq
+        achieved_tf = flop_per_launch / (launch_ms * 1e-3) / 1e12
+        peak_tf = max(fp32["ffma2_tflops"], fp32["ffma_tflops"])
+        # algorithmic HBM bytes per launch: IQ read once + float audio write + phase table read
+        bytes_per_launch = n_iq * 8 + a.channels * (n_iq // 16) * (4 + 8)
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:  # noqa: BLE001
+            hbm_peak = 6650.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "demod_fast_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:  # noqa: BLE001
+            pass
+        roofline = dict(bound="fp32_fma_pipe", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
+                        frac=achieved_tf / peak_tf, traffic=traffic,
+                        kernel="demod_fast_kernel<16,4,128>" if a.mode == "fast" else "demod_exact_kernel<16>",
+                        launch_ms=launch_ms, launches_timed=demod_launches,
+                        kernel_share_of_step=demod_ms / (ms_total if ms_total > 0 else 1),
+                        peak_source="FFMA2 register-resident microbenchmark run in this process "
+                                    "(cwsl_measure_fp32_peak); MEASURED_PEAKS.json has no FP32-pipe figure. "
+                                    f"Nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; plain FFMA "
+                                    f"measured {fp32['ffma_tflops']:.1f}",
+                        algorithmic="134 flop per channel-sample (SURVEY.md 8d) x channels x IQ samples per launch",
+                        hbm=dict(achieved_gbs=bytes_per_launch / (launch_ms * 1e-3) / 1e9, peak_gbs=hbm_peak,
+                                 frac=bytes_per_launch / (launch_ms * 1e-3) / 1e9 / hbm_peak,
+                                 bytes_per_launch=bytes_per_launch, peak_source="MEASURED_PEAKS.json hbm_gbs"))
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            n_ch = int(min(a.channels, max(32, 4 * cores)))
+            sub = freqs[:: max(1, a.channels // n_ch)][:n_ch].astype(np.int32)
+            cpu = cpu_chain(sub, n_blocks, a.cpu_seconds, fast=True)
+            strict = cpu_chain(sub[: max(8, cores)], n_blocks, a.cpu_seconds / 2, fast=False, max_reps=3)
+            cpu["strict_build"] = dict(value=strict["value"], seconds=strict.get("seconds"), sample=strict["sample"])
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(3, a.warmup),
+                    ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
+                    data="synthetic",
+                    config=dict(workload=workload_name(a), receivers_total=a.receivers, channels=a.channels,
+                                receivers_per_rank=len(my_rx), sample_rate=FS, iq_len=IQ_LEN, slot_s=PERIOD,
+                                mode=a.mode, parallelism=f"receiver-sharded x{world}, no data-path collective",
+                                l2="inputs larger than L2: every launch reads a different receiver's 23 MB IQ and "
+                                   "writes 737 MB of float audio; a step touches > 60 GB"),
+                    x_realtime_per_gpu=PERIOD * len(my_rx) / (ms_step * 1e-3),
+                    gchs_per_gpu=value / 1e3 / world,
+                    clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
+                    kernel_ms=dict(demod=demod_ms, quantise_and_clear=quant_ms, event_total=ms_total),
+                    gathered_checksums=gathered)
+        print(json.dumps(line), flush=True)
+    for rx in rxs:
+        rx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,8 +16,8 @@ SYMBOLS = [
     "cwsl_af_size", "cwsl_accepted_blocks", "cwsl_rx_create", "cwsl_rx_destroy", "cwsl_rx_set_mode",
     "cwsl_rx_add_group", "cwsl_rx_add_channel", "cwsl_rx_num_groups", "cwsl_rx_num_channels",
     "cwsl_rx_group_af_size", "cwsl_rx_push_iq", "cwsl_rx_push_iq_device", "cwsl_rx_bind_device_iq",
-    "cwsl_rx_process", "cwsl_rx_end_slot", "cwsl_rx_device_audio", "cwsl_rx_read_float_audio",
-    "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_stream", "cwsl_rx_enable_timing",
+    "cwsl_rx_process", "cwsl_rx_end_slot", "cwsl_rx_device_audio", "cwsl_rx_copy_device_audio", "cwsl_rx_read_float_audio",
+    "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_stream", "cwsl_rx_set_stream", "cwsl_rx_enable_timing",
     "cwsl_rx_kernel_times", "cwsl_measure_fp32_peak",
 ]
 
@@ -80,11 +80,13 @@ def lib() -> C.CDLL:
     L.cwsl_rx_end_slot.argtypes = [vp, C.c_int, vp, C.POINTER(sz)]
     L.cwsl_rx_device_audio.restype = vp
     L.cwsl_rx_device_audio.argtypes = [vp, C.c_int]
+    L.cwsl_rx_copy_device_audio.argtypes = [vp, C.c_int, C.c_int, vp]
     L.cwsl_rx_read_float_audio.argtypes = [vp, C.c_int, C.c_int, vp]
     L.cwsl_rx_channel_stats.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.cwsl_rx_synchronize.argtypes = [vp]
     L.cwsl_rx_stream.restype = vp
     L.cwsl_rx_stream.argtypes = [vp]
+    L.cwsl_rx_set_stream.argtypes = [vp, vp]
     L.cwsl_rx_enable_timing.argtypes = [vp, C.c_int]
     L.cwsl_rx_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int)]
@@ -217,6 +219,9 @@ class Receiver:
     def device_audio(self, group: int) -> int:
         return self._L.cwsl_rx_device_audio(self._h, group)
 
+    def copy_device_audio(self, group: int, channel: int, dptr: int) -> None:
+        _check(self._L.cwsl_rx_copy_device_audio(self._h, group, channel, dptr))
+
     def read_float_audio(self, group: int, channel: int) -> np.ndarray:
         out = np.empty(self.group_af_size(group), np.float32)
         _check(self._L.cwsl_rx_read_float_audio(self._h, group, channel, out.ctypes.data))
@@ -229,6 +234,9 @@ class Receiver:
 
     def synchronize(self) -> None:
         _check(self._L.cwsl_rx_synchronize(self._h))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        _check(self._L.cwsl_rx_set_stream(self._h, cuda_stream))
 
     def stream(self) -> int:
         return self._L.cwsl_rx_stream(self._h)

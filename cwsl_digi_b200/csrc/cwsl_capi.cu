@@ -102,6 +102,7 @@ struct cwsl_rx {
     int mode = CWSL_MODE_FAST;
     double ring_seconds = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     float2* d_ring = nullptr;        // owned ring (nullptr while bound to external IQ)
     const float2* ring_ptr = nullptr;  // what the kernels read
     uint32_t ring_blocks = 0;
@@ -488,13 +489,23 @@ void cwsl_rx_destroy(cwsl_rx_t* rx) {
         cudaEventDestroy(pr.second);
     }
     for (auto e : rx->ev_pool) cudaEventDestroy(e);
-    if (rx->stream) cudaStreamDestroy(rx->stream);
+    if (rx->stream && rx->own_stream) cudaStreamDestroy(rx->stream);
     delete rx;
 }
 
 int cwsl_rx_set_mode(cwsl_rx_t* rx, int mode) {
     if (!rx || (mode != CWSL_MODE_EXACT && mode != CWSL_MODE_FAST)) return fail(CWSL_ERR_INVALID, "bad mode %d", mode);
     rx->mode = mode;
+    return CWSL_OK;
+}
+
+int cwsl_rx_set_stream(cwsl_rx_t* rx, void* cuda_stream) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    DeviceGuard dg(rx->device);
+    CK(cudaStreamSynchronize(rx->stream));
+    if (rx->own_stream && rx->stream) cudaStreamDestroy(rx->stream);
+    rx->stream = static_cast<cudaStream_t>(cuda_stream);
+    rx->own_stream = false;
     return CWSL_OK;
 }
 
@@ -641,6 +652,17 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
 const int16_t* cwsl_rx_device_audio(const cwsl_rx_t* rx, int group) {
     if (!rx || group < 0 || group >= (int)rx->groups.size()) return nullptr;
     return rx->groups[group].d_out;
+}
+
+int cwsl_rx_copy_device_audio(cwsl_rx_t* rx, int group, int channel, int16_t* d_dst) {
+    Group* g = get_group(rx, group);
+    if (!g || !d_dst) return fail(CWSL_ERR_INVALID, "bad arguments");
+    if (!g->have_result) return fail(CWSL_ERR_STATE, "no finished slot available");
+    if (channel < 0 || channel >= (int)g->ch.size()) return fail(CWSL_ERR_INVALID, "bad channel %d", channel);
+    DeviceGuard dg(rx->device);
+    CK(cudaMemcpyAsync(d_dst, g->d_out + (size_t)channel * g->af_size, g->af_size * sizeof(int16_t),
+                       cudaMemcpyDeviceToDevice, rx->stream));
+    return CWSL_OK;
 }
 
 int cwsl_rx_read_float_audio(cwsl_rx_t* rx, int group, int channel, float* out) {

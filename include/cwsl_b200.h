@@ -136,6 +136,11 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
  * the next cwsl_rx_end_slot on the same group. */
 const int16_t* cwsl_rx_device_audio(const cwsl_rx_t* rx, int group);
 
+/* Copy one channel's int16 audio of the last finished slot (af_size samples) into the caller's
+ * DEVICE buffer, asynchronously on the receiver's stream (e.g. as the send buffer of an NCCL
+ * gather of per-slot audio to the station's rank 0). */
+int cwsl_rx_copy_device_audio(cwsl_rx_t* rx, int group, int channel, int16_t* d_dst);
+
 /* Float audio before normalisation of the last finished slot (what prepareAudio reads,
  * source/Instance.cpp:295), copied to HOST out[af_size] (zero tail included); synchronous.
  * Parity/debug aid. */
@@ -150,6 +155,11 @@ int cwsl_rx_synchronize(cwsl_rx_t* rx);
 
 /* The CUDA stream (cudaStream_t) all work of this receiver is queued on, for event timing. */
 void* cwsl_rx_stream(cwsl_rx_t* rx);
+
+/* Queue all further work of this receiver on the caller's stream (cudaStream_t; NULL = the legacy
+ * default stream) instead of the private one, e.g. to order it with the caller's own copies and
+ * events. The receiver never destroys a caller-supplied stream. */
+int cwsl_rx_set_stream(cwsl_rx_t* rx, void* cuda_stream);
 
 /* Record CUDA events around every kernel launch of this receiver (off by default). */
 int cwsl_rx_enable_timing(cwsl_rx_t* rx, int on);

@@ -182,11 +182,11 @@ void oracle_quantise(const float* buf, size_t size, int16_t* out) {
 
 /* Whole chain for one decoder, one slot (steady-state reset, source/Instance.cpp:251).
  * Returns write_index (audio samples produced), or (size_t)-1 on invalid tuning. */
-size_t oracle_slot(uint32_t fs, int32_t demod_freq, const float* iq, size_t n_iq, size_t iq_len,
-                   float scale, size_t af_size, float* af_raw /*nullable, af_size*/, int16_t* out_i16,
-                   float* max_out, float* factor_out) {
+size_t oracle_slot_sb(uint32_t fs, int32_t demod_freq, int is_usb, const float* iq, size_t n_iq, size_t iq_len,
+                      float scale, size_t af_size, float* af_raw /*nullable, af_size*/, int16_t* out_i16,
+                      float* max_out, float* factor_out) {
     oracle_tables_t t;
-    if (oracle_tables_build(&t, fs, demod_freq, 1) != 0) return (size_t)-1;
+    if (oracle_tables_build(&t, fs, demod_freq, is_usb) != 0) return (size_t)-1;
     const size_t dec = fs / WAVE_SR;                                            /* Instance.cpp:192 */
     const size_t acc = oracle_accepted_blocks(n_iq, iq_len, dec, af_size);
     const size_t n_blocks = acc * iq_len / t.block_size;
@@ -201,6 +201,13 @@ size_t oracle_slot(uint32_t fs, int32_t demod_freq, const float* iq, size_t n_iq
     free(af);
     oracle_tables_free(&t);
     return n_blocks;
+}
+
+size_t oracle_slot(uint32_t fs, int32_t demod_freq, const float* iq, size_t n_iq, size_t iq_len,
+                   float scale, size_t af_size, float* af_raw, int16_t* out_i16, float* max_out,
+                   float* factor_out) {
+    return oracle_slot_sb(fs, demod_freq, 1 /* USB, source/CWSL_DIGI.hpp:53 */, iq, n_iq, iq_len, scale, af_size,
+                          af_raw, out_i16, max_out, factor_out);
 }
 
 /* Flat accessor for ctypes: filter[filt_order], tone[2*block_size], phase_inc[2], raw sum. */

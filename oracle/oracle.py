@@ -43,6 +43,9 @@ class Port:
         lib.oracle_slot.restype = C.c_size_t
         lib.oracle_slot.argtypes = [C.c_uint32, C.c_int32, _f32p, C.c_size_t, C.c_size_t, C.c_float,
                                     C.c_size_t, C.c_void_p, _i16p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        lib.oracle_slot_sb.restype = C.c_size_t
+        lib.oracle_slot_sb.argtypes = [C.c_uint32, C.c_int32, C.c_int, _f32p, C.c_size_t, C.c_size_t, C.c_float,
+                                       C.c_size_t, C.c_void_p, _i16p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         lib.oracle_tables_flat.restype = C.c_int
         lib.oracle_tables_flat.argtypes = [C.c_uint32, C.c_int32, C.c_int, _f32p, _f32p, _f32p,
                                            C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
@@ -51,14 +54,14 @@ class Port:
         lib.oracle_accepted_blocks.restype = C.c_size_t
         lib.oracle_accepted_blocks.argtypes = [C.c_size_t] * 4
 
-    def slot(self, fs, demod_freq, iq, iq_len, scale, afsize, want_raw=True):
+    def slot(self, fs, demod_freq, iq, iq_len, scale, afsize, want_raw=True, is_usb=True):
         iq = np.ascontiguousarray(iq, dtype=np.float32).reshape(-1)
         n_iq = iq.size // 2
         out = np.zeros(afsize, np.int16)
         raw = np.zeros(afsize, np.float32) if want_raw else None
         mx, fac = C.c_float(), C.c_float()
-        wi = self.lib.oracle_slot(fs, demod_freq, iq, n_iq, iq_len, scale, afsize,
-                                  raw.ctypes.data if want_raw else None, out, C.byref(mx), C.byref(fac))
+        wi = self.lib.oracle_slot_sb(fs, demod_freq, int(is_usb), iq, n_iq, iq_len, scale, afsize,
+                                     raw.ctypes.data if want_raw else None, out, C.byref(mx), C.byref(fac))
         if wi == C.c_size_t(-1).value:
             raise ValueError("invalid tuning")
         return dict(write_index=wi, i16=out, raw=raw, max=mx.value, factor=fac.value)
@@ -99,6 +102,9 @@ class Ref:
         lib.cwsl_ref_slot.restype = C.c_size_t
         lib.cwsl_ref_slot.argtypes = [C.c_uint32, C.c_int32, _f32p, C.c_size_t, C.c_size_t, C.c_float,
                                       C.c_size_t, C.c_void_p, _i16p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        lib.cwsl_ref_slot_sb.restype = C.c_size_t
+        lib.cwsl_ref_slot_sb.argtypes = [C.c_uint32, C.c_int32, C.c_int, _f32p, C.c_size_t, C.c_size_t, C.c_float,
+                                         C.c_size_t, C.c_void_p, _i16p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         lib.cwsl_ref_tables.restype = C.c_size_t
         lib.cwsl_ref_tables.argtypes = [C.c_uint32, C.c_int32, C.c_int, _f32p, _f32p, _f32p, C.POINTER(C.c_float)]
         lib.cwsl_ref_phase_after.restype = None
@@ -111,14 +117,14 @@ class Ref:
                                                C.POINTER(C.c_uint64)]
         lib.cwsl_ref_hardware_concurrency.restype = C.c_uint
 
-    def slot(self, fs, demod_freq, iq, iq_len, scale, afsize, want_raw=True):
+    def slot(self, fs, demod_freq, iq, iq_len, scale, afsize, want_raw=True, is_usb=True):
         iq = np.ascontiguousarray(iq, dtype=np.float32).reshape(-1)
         n_iq = iq.size // 2
         out = np.zeros(afsize, np.int16)
         raw = np.zeros(afsize, np.float32) if want_raw else None
         mx, fac = C.c_float(), C.c_float()
-        wi = self.lib.cwsl_ref_slot(fs, demod_freq, iq, n_iq, iq_len, scale, afsize,
-                                    raw.ctypes.data if want_raw else None, out, C.byref(mx), C.byref(fac))
+        wi = self.lib.cwsl_ref_slot_sb(fs, demod_freq, int(is_usb), iq, n_iq, iq_len, scale, afsize,
+                                       raw.ctypes.data if want_raw else None, out, C.byref(mx), C.byref(fac))
         if wi == C.c_size_t(-1).value:
             raise ValueError("invalid tuning")
         return dict(write_index=wi, i16=out, raw=raw, max=mx.value, factor=fac.value)

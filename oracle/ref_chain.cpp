@@ -37,8 +37,8 @@ const float kAudioClip = std::pow(2.0f, 15.0f) - 1.0f;  // source/CWSL_DIGI.hpp:
 
 // source/Instance.cpp:259-277 for a whole slot worth of blocks
 size_t demod_slot(uint32_t fs, int32_t demod_freq, const std::complex<float>* iq, size_t n_iq,
-                  size_t iq_len, float* af, size_t af_size) {
-    SSBD<float> ssbd(fs, kSSBBW, static_cast<float>(demod_freq), kUSB);
+                  size_t iq_len, float* af, size_t af_size, bool usb = kUSB) {
+    SSBD<float> ssbd(fs, kSSBBW, static_cast<float>(demod_freq), usb);
     const size_t dec_ratio = fs / kWaveSR;               // Instance.cpp:192
     const size_t in_size = ssbd.GetInSize();
     size_t write_index = 0;
@@ -82,6 +82,24 @@ size_t cwsl_ref_slot(uint32_t fs, int32_t demod_freq, const float* iq_interleave
         prepare_audio(af.data(), af_size, scale, max_out, factor_out);
         for (size_t k = 0; k < af_size; ++k)
             out_i16[k] = static_cast<int16_t>(af[k] + 0.5f);            // Instance.cpp:238-241
+        return wi;
+    } catch (const std::exception&) {
+        return static_cast<size_t>(-1);
+    }
+}
+
+// Same chain with the sideband selectable (the application always passes USB, source/CWSL_DIGI.hpp:53;
+// SSBD itself supports LSB, source/SSBD.hpp:48,110).
+size_t cwsl_ref_slot_sb(uint32_t fs, int32_t demod_freq, int is_usb, const float* iq_interleaved, size_t n_iq,
+                        size_t iq_len, float scale, size_t af_size, float* af_raw, int16_t* out_i16,
+                        float* max_out, float* factor_out) {
+    try {
+        std::vector<float> af(af_size, 0.0f);
+        const auto* iq = reinterpret_cast<const std::complex<float>*>(iq_interleaved);
+        const size_t wi = demod_slot(fs, demod_freq, iq, n_iq, iq_len, af.data(), af_size, is_usb != 0);
+        if (af_raw) std::memcpy(af_raw, af.data(), af_size * sizeof(float));
+        prepare_audio(af.data(), af_size, scale, max_out, factor_out);
+        for (size_t k = 0; k < af_size; ++k) out_i16[k] = static_cast<int16_t>(af[k] + 0.5f);
         return wi;
     } catch (const std::exception&) {
         return static_cast<size_t>(-1);

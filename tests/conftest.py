@@ -1,0 +1,51 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def port():
+    from oracle.oracle import Port
+    return Port()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference's own headers compiled into oracle/_ref (prebuilt here; travels to the GPU box)."""
+    from oracle.oracle import Ref
+    try:
+        return Ref()
+    except (FileNotFoundError, OSError, Exception) as e:  # noqa: BLE001
+        pytest.skip(f"oracle/_ref unavailable: {e}")
+
+
+@pytest.fixture(scope="session")
+def cw():
+    import cwsl_digi_b200 as cw
+    if not os.path.exists(cw.lib_path()):
+        cw.build_library()
+    return cw
+
+
+def has_gpu():
+    try:
+        import cwsl_digi_b200 as cw
+        return cw.device_count() > 0
+    except Exception:  # noqa: BLE001
+        return False
+
+
+@pytest.fixture(scope="session")
+def gpu(cw):
+    if cw.device_count() <= 0:
+        pytest.fail("no CUDA device: the product has no CPU path, -m gpu tests need the B200 box")
+    return cw

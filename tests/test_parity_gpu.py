@@ -1,0 +1,377 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libcwsl_b200.so), against the oracle
+(the reference's own headers compiled into oracle/_ref, and the committed golden vectors).
+
+Bars (BASELINE.json north_star):
+  EXACT mode: float audio and int16 output bit-identical to the reference chain.
+  FAST mode:  |int16 diff| <= 1 LSB and float residual >= 90 dB below the signal.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from cwsl_digi_b200 import synth
+from oracle.oracle import af_size
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+FAST_MAX_LSB = 1          # tolerance stated by north_star
+FAST_MIN_RESID_DB = 90.0  # residual must be at least this far below the signal
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def resid_db(got, want):
+    want = want.astype(np.float64)
+    err = got.astype(np.float64) - want
+    sig = np.sqrt(np.mean(want ** 2))
+    return 20 * np.log10(max(np.sqrt(np.mean(err ** 2)), 1e-300) / sig)
+
+
+def run_slot(cw, fs, iq_len, period, chans, iq, mode, ring_seconds=0.0, chunks=None, usb=True):
+    """One slot through the C ABI. chans = [(freq, scale)]. Returns (i16[n_ch, af], raw[n_ch, af], wi, stats)."""
+    with cw.Receiver(0, fs, iq_len, ring_seconds=ring_seconds, mode=mode) as rx:
+        g = rx.add_group(period)
+        for f, sc in chans:
+            rx.add_channel(g, f, sc, is_usb=usb)
+        iq = np.ascontiguousarray(iq, np.float32).reshape(-1)
+        nblk = iq.size // (2 * iq_len)
+        if chunks is None:
+            rx.push_iq(iq)
+        else:
+            pos = 0
+            for i, c in enumerate(chunks):
+                c = min(c, nblk - pos)
+                if c <= 0:
+                    break
+                rx.push_iq(iq[pos * iq_len * 2:(pos + c) * iq_len * 2])
+                pos += c
+                if i % 2 == 0:
+                    rx.process(g)
+            if pos < nblk:
+                rx.push_iq(iq[pos * iq_len * 2:])
+        out, wi = rx.end_slot_numpy(g)
+        raw = np.stack([rx.read_float_audio(g, c) for c in range(len(chans))])
+        stats = [rx.channel_stats(g, c) for c in range(len(chans))]
+    return out, raw, wi, stats
+
+
+def check_exact(out, raw, wi, stats, want):
+    for c, o in enumerate(want):
+        assert wi == o["write_index"]
+        assert np.array_equal(_bits(raw[c]), _bits(o["raw"])), f"channel {c}: float audio not bit-identical"
+        assert np.array_equal(out[c], o["i16"]), f"channel {c}: int16 not identical"
+        assert stats[c][0] == o["max"] and stats[c][1] == o["factor"]
+
+
+def check_fast(out, raw, wi, stats, want):
+    for c, o in enumerate(want):
+        assert wi == o["write_index"]
+        d = np.abs(out[c].astype(np.int32) - o["i16"].astype(np.int32))
+        assert d.max() <= FAST_MAX_LSB, f"channel {c}: {d.max()} LSB"
+        assert not out[c][wi:].any()
+        r = resid_db(raw[c][:wi], o["raw"][:wi])
+        assert r <= -FAST_MIN_RESID_DB, f"channel {c}: residual {r:.1f} dB"
+        assert abs(stats[c][0] - o["max"]) <= 1e-5 * o["max"]
+
+
+# ---- golden vectors ------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_golden(gpu, path, mode):
+    cw = gpu
+    g = np.load(path)
+    fs, iq_len, afs = int(g["fs"]), int(g["iq_len"]), int(g["af_size"])
+    chans = [(int(f), float(s)) for f, s in zip(g["freqs"], g["scales"])]
+    out, raw, wi, stats = run_slot(cw, fs, iq_len, float(g["period"]), chans, g["iq"],
+                                   cw.MODE_EXACT if mode == "exact" else cw.MODE_FAST)
+    want = []
+    for c in range(len(chans)):
+        w = int(g["write_index"][c])
+        i16 = np.zeros(afs, np.int16)
+        i16[:w] = g["i16"][c]
+        rw = np.zeros(afs, np.float32)
+        rw[:w] = g["raw"][c]
+        want.append(dict(write_index=w, i16=i16, raw=rw, max=float(g["maxval"][c]), factor=float(g["factor"][c])))
+    (check_exact if mode == "exact" else check_fast)(out, raw, wi, stats, want)
+
+
+# ---- BASELINE.json configs[0]: one 192 kHz receiver, FT8 @ 14074000, one full 15 s slot ------------
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_config1_full_ft8_slot(gpu, ref, mode):
+    cw = gpu
+    fs, iq_len = 192000, 2048
+    lo, dial = 14100000, 14074000
+    demod = dial - lo
+    n = 15 * fs // iq_len * iq_len
+    iq = synth.receiver_iq(n, fs, [demod], receiver=0)
+    out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, [(demod, 0.9)], iq,
+                                   cw.MODE_EXACT if mode == "exact" else cw.MODE_FAST)
+    o = ref.slot(fs, demod, iq, iq_len, 0.9, af_size(15))
+    assert wi == 179968
+    (check_exact if mode == "exact" else check_fast)(out, raw, wi, stats, [o])
+
+
+# ---- streaming: chunked pushes through a small ring == one shot ---------------------------------
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("fs,iq_len", [(192000, 2048), (192000, 512), (96000, 1024), (48000, 512)])
+def test_streaming_small_ring(gpu, ref, mode, fs, iq_len):
+    cw = gpu
+    freq = -fs // 8
+    nblk = 3 * fs // iq_len
+    iq = synth.receiver_iq(nblk * iq_len, fs, [freq], receiver=5, tones_per_channel=2)
+    rng = np.random.default_rng(iq_len)
+    chunks = list(rng.integers(1, 12, 2000))
+    out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, [(freq, 0.9)], iq,
+                                   cw.MODE_EXACT if mode == "exact" else cw.MODE_FAST,
+                                   ring_seconds=0.25, chunks=chunks)
+    o = ref.slot(fs, freq, iq, iq_len, 0.9, af_size(15))
+    (check_exact if mode == "exact" else check_fast)(out, raw, wi, stats, [o])
+
+
+# ---- slot purity / steady-state reset (Instance.cpp:251) and two groups with different edges ------
+def test_consecutive_slots_and_two_groups(gpu, ref):
+    cw = gpu
+    fs, iq_len = 192000, 2048
+    per_a, per_b = 2, 3   # IQ "superblocks" per slot for the two groups
+    unit = 20             # IQ blocks per superblock
+    total = 6 * unit
+    fa, fb = -26000, -20000
+    iq = synth.receiver_iq(total * iq_len, fs, [fa, fb], receiver=9, tones_per_channel=2)
+    with cw.Receiver(0, fs, iq_len, ring_seconds=1.0, mode=cw.MODE_EXACT) as rx:
+        ga = rx.add_group(15.0)
+        gb = rx.add_group(7.5)
+        rx.add_channel(ga, fa, 0.9)
+        rx.add_channel(gb, fb, 0.9)
+        got_a, got_b = [], []
+        for sb in range(6):
+            rx.push_iq(iq[sb * unit * iq_len * 2:(sb + 1) * unit * iq_len * 2])
+            if (sb + 1) % per_a == 0:
+                got_a.append(rx.end_slot_numpy(ga))
+            if (sb + 1) % per_b == 0:
+                got_b.append(rx.end_slot_numpy(gb))
+    assert len(got_a) == 3 and len(got_b) == 2
+    for i, (out, wi) in enumerate(got_a):
+        span = iq[i * per_a * unit * iq_len * 2:(i + 1) * per_a * unit * iq_len * 2]
+        o = ref.slot(fs, fa, span, iq_len, 0.9, af_size(15))
+        assert wi == o["write_index"] and np.array_equal(out[0], o["i16"])
+    for i, (out, wi) in enumerate(got_b):
+        span = iq[i * per_b * unit * iq_len * 2:(i + 1) * per_b * unit * iq_len * 2]
+        o = ref.slot(fs, fb, span, iq_len, 0.9, af_size(7.5))
+        assert wi == o["write_index"] and np.array_equal(out[0], o["i16"])
+
+
+def test_empty_slot_is_all_zero(gpu):
+    cw = gpu
+    with cw.Receiver(0, 192000, 2048, mode=cw.MODE_FAST) as rx:
+        g = rx.add_group(15.0)
+        rx.add_channel(g, -26000, 0.9)
+        out, wi = rx.end_slot_numpy(g)
+        assert wi == 0 and not out.any()
+        mx, fac = rx.channel_stats(g, 0)
+        assert mx == 0.0 and fac == np.float32(np.float32(32767.0) / np.float32(1.0)) * np.float32(0.9)
+
+
+def test_af_buffer_full_guard(gpu, ref):
+    # FT4 buffer (150000 samples) fed 13 s of IQ: the guard (Instance.cpp:268-271) drops the excess
+    cw = gpu
+    fs, iq_len = 192000, 4096
+    nblk = 13 * fs // iq_len
+    iq = synth.receiver_iq(nblk * iq_len, fs, [-20000], receiver=2, tones_per_channel=1)
+    out, raw, wi, stats = run_slot(cw, fs, iq_len, 7.5, [(-20000, 0.9)], iq, cw.MODE_EXACT)
+    o = ref.slot(fs, -20000, iq, iq_len, 0.9, af_size(7.5))
+    assert wi == o["write_index"] < nblk * iq_len // 16
+    check_exact(out, raw, wi, stats, [o])
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_lsb_channel(gpu, ref, mode):
+    cw = gpu
+    fs, iq_len = 192000, 2048
+    iq = synth.receiver_iq(30 * iq_len, fs, [20000], receiver=4, tones_per_channel=2)
+    out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, [(26000, 0.9)], iq,
+                                   cw.MODE_EXACT if mode == "exact" else cw.MODE_FAST, usb=False)
+    o = ref.slot(fs, 26000, iq, iq_len, 0.9, af_size(15), is_usb=False)
+    (check_exact if mode == "exact" else check_fast)(out, raw, wi, stats, [o])
+
+
+# ---- BASELINE.json configs[1]: the default 20 m decoder set on one receiver ----------------------
+def test_config2_default_20m_set(gpu, ref):
+    cw = gpu
+    fs, iq_len, lo = 192000, 2048, 14100000
+    decs = [(14095600, "WSPR", 120.0, 0.20), (14090000, "FT8", 15.0, 0.90), (14080000, "FT4", 7.5, 0.90),
+            (14074000, "FT8", 15.0, 0.90), (14076000, "JT65", 60.0, 0.90), (14078000, "JS8", 15.0, 0.90),
+            (14097000, "FST4W-120", 120.0, 0.90)]
+    n = 8 * fs // iq_len * iq_len      # 8 s of IQ feeds every mode (FT4 takes its first 7.5 s slot)
+    iq = synth.receiver_iq(n, fs, [d[0] - lo for d in decs], receiver=1, tones_per_channel=2)
+    for mode, chk in ((cw.MODE_EXACT, check_exact), (cw.MODE_FAST, check_fast)):
+        with cw.Receiver(0, fs, iq_len, mode=mode) as rx:
+            groups = {}
+            where = []
+            for dial, m, per, sc in decs:
+                if per not in groups:
+                    groups[per] = rx.add_group(per)
+                where.append((groups[per], rx.add_channel(groups[per], dial - lo, sc)))
+            nb_ft4 = int(7.5 * fs) // iq_len
+            rx.push_iq(iq[:nb_ft4 * iq_len * 2])
+            ft4_out, ft4_wi = rx.end_slot_numpy(groups[7.5])
+            ft4_raw = rx.read_float_audio(groups[7.5], 0)
+            ft4_stats = rx.channel_stats(groups[7.5], 0)
+            rx.push_iq(iq[nb_ft4 * iq_len * 2:])
+            res = {}
+            for per, g in groups.items():
+                if per == 7.5:
+                    continue
+                out, wi = rx.end_slot_numpy(g)
+                res[g] = (out, wi, [rx.read_float_audio(g, c) for c in range(out.shape[0])],
+                          [rx.channel_stats(g, c) for c in range(out.shape[0])])
+        for (dial, m, per, sc), (g, c) in zip(decs, where):
+            if per == 7.5:
+                o = ref.slot(fs, dial - lo, iq[:nb_ft4 * iq_len * 2], iq_len, sc, af_size(per))
+                chk(ft4_out, ft4_raw[None], ft4_wi, [ft4_stats], [o])
+            else:
+                o = ref.slot(fs, dial - lo, iq, iq_len, sc, af_size(per))
+                out, wi, raws, stats = res[g]
+                chk(out[c:c + 1], np.stack(raws)[c:c + 1], wi, stats[c:c + 1], [o])
+
+
+# ---- long slot: WSPR 120 s, phase table exact over 1.44 M steps (BASELINE.json configs[3]) -------
+def test_wspr_120s_exact(gpu, ref):
+    import torch
+    cw = gpu
+    fs, iq_len = 192000, 2048
+    nblk = 120 * fs // iq_len
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = (torch.randn(nblk * iq_len * 2, device="cuda", generator=g) * 300.0)
+    t = torch.arange(nblk * iq_len, device="cuda", dtype=torch.float64)
+    ph = 2 * np.pi * ((-4400 + 1500) * t % fs) / fs
+    x[0::2] += (8000 * torch.cos(ph)).float()
+    x[1::2] += (8000 * torch.sin(ph)).float()
+    iq = x.cpu().numpy()
+    with cw.Receiver(0, fs, iq_len, ring_seconds=2.0, mode=cw.MODE_EXACT) as rx:
+        grp = rx.add_group(120.0)
+        rx.add_channel(grp, -4400, 0.20)
+        step = 400
+        for b in range(0, nblk, step):          # device-to-device pushes through a 2 s ring
+            nb = min(step, nblk - b)
+            rx.push_iq_device(x.data_ptr() + b * iq_len * 8, nb)
+        out, wi = rx.end_slot_numpy(grp)
+        raw = rx.read_float_audio(grp, 0)
+    o = ref.slot(fs, -4400, iq, iq_len, 0.20, af_size(120))
+    assert wi == o["write_index"] == nblk * iq_len // 16
+    assert np.array_equal(_bits(raw), _bits(o["raw"]))
+    assert np.array_equal(out[0], o["i16"])
+
+
+# ---- properties at BASELINE's full size: 1024 channels x one FT8 slot, resident IQ ---------------
+@pytest.fixture(scope="module")
+def stress_run(gpu):
+    import torch
+    cw = gpu
+    fs, iq_len = 192000, 2048
+    nblk = 15 * fs // iq_len
+    freqs = synth.stress_demod_freqs(1024)
+    g = torch.Generator(device="cuda").manual_seed(20261017)
+    x = torch.randn(nblk * iq_len * 2, device="cuda", generator=g) * 300.0
+    t = torch.arange(nblk * iq_len, device="cuda", dtype=torch.float64)
+    for j, f in enumerate(freqs[::64]):
+        ph = 2 * np.pi * ((int(f) + 700 + 100 * j) * t % fs) / fs
+        x[0::2] += (4000 * torch.cos(ph)).float()
+        x[1::2] += (4000 * torch.sin(ph)).float()
+
+    def run(xdev, order, mode=cw.MODE_FAST):
+        with cw.Receiver(0, fs, iq_len, mode=mode) as rx:
+            grp = rx.add_group(15.0)
+            for f in freqs[order]:
+                rx.add_channel(grp, int(f), 0.9)
+            rx.bind_device_iq(xdev.data_ptr(), nblk)
+            host, wi = rx.end_slot_numpy(grp)
+            raws = {c: rx.read_float_audio(grp, c) for c in (0, 1, 511, 1023)}
+        return host, wi, raws
+
+    return dict(cw=cw, fs=fs, iq_len=iq_len, nblk=nblk, freqs=freqs, x=x, run=run)
+
+
+def test_stress_properties(stress_run, ref):
+    s = stress_run
+    cw, freqs, x, nblk, fs, iq_len = s["cw"], s["freqs"], s["x"], s["nblk"], s["fs"], s["iq_len"]
+    order = np.arange(1024)
+    base, wi, raws = s["run"](x, order)
+    assert wi == 179968
+    # idempotence / slot purity: same IQ, fresh receiver -> identical bytes
+    again, _, _ = s["run"](x, order)
+    assert np.array_equal(base, again)
+    # channel-order independence: a permuted channel list gives the permuted result, bit for bit
+    perm = np.random.default_rng(0).permutation(1024)
+    permuted, _, _ = s["run"](x, perm)
+    assert np.array_equal(permuted, base[perm])
+    # homogeneity: IQ * 2 (exact in binary floating point) doubles the float audio exactly
+    _, _, raws2 = s["run"](x * 2.0, order)
+    for c in raws:
+        assert np.array_equal(_bits(raws2[c]), _bits(raws[c] * np.float32(2.0)))
+    # zero tail and headroom: |q| <= 0.9*32767, tail all zero
+    assert not base[:, wi:].any()
+    assert np.abs(base.astype(np.int32)).max() <= int(0.9 * 32767) + 1
+    assert (np.abs(base.astype(np.int32)).max(axis=1) >= int(0.9 * 32767) - 2).all()
+    # spot-check channels of the full-size run against the reference chain (fast-mode bars)
+    iq = x.cpu().numpy()
+    for c in (0, 511, 1023):
+        o = ref.slot(fs, int(freqs[c]), iq, iq_len, 0.9, af_size(15))
+        d = np.abs(base[c].astype(np.int32) - o["i16"].astype(np.int32))
+        assert d.max() <= FAST_MAX_LSB
+        assert resid_db(raws[c][:wi], o["raw"][:wi]) <= -FAST_MIN_RESID_DB
+
+
+def test_stress_exact_spot_channels(stress_run, ref):
+    s = stress_run
+    cw, freqs, x, nblk, fs, iq_len = s["cw"], s["freqs"], s["x"], s["nblk"], s["fs"], s["iq_len"]
+    sel = [0, 300, 1023]
+    with cw.Receiver(0, fs, iq_len, mode=cw.MODE_EXACT) as rx:
+        grp = rx.add_group(15.0)
+        for c in sel:
+            rx.add_channel(grp, int(freqs[c]), 0.9)
+        rx.bind_device_iq(x.data_ptr(), nblk)
+        out, wi = rx.end_slot_numpy(grp)
+    iq = x.cpu().numpy()
+    for i, c in enumerate(sel):
+        o = ref.slot(fs, int(freqs[c]), iq, iq_len, 0.9, af_size(15))
+        assert np.array_equal(out[i], o["i16"])
+
+
+# ---- error behaviour mirrors the reference's exceptions / config checks --------------------------
+def test_error_behaviour(gpu):
+    cw = gpu
+    with pytest.raises(cw.CwslError):
+        cw.Receiver(0, 100000, 2048)            # SSBD.hpp:54
+    with pytest.raises(cw.CwslError):
+        cw.Receiver(0, 192000, 1000)            # iq_len not a multiple of GetInSize()
+    with pytest.raises(cw.CwslError):
+        cw.Receiver(99, 192000, 2048)
+    with cw.Receiver(0, 192000, 2048) as rx:
+        with pytest.raises(cw.CwslError) as e:
+            rx.push_iq(np.zeros(2048 * 2, np.float32))      # no group yet
+        assert e.value.code == -4
+        g = rx.add_group(15.0)
+        with pytest.raises(cw.CwslError) as e:
+            rx.add_channel(g, 90001, 0.9)                   # SSBD.hpp:102 "Signal outside of band (high)"
+        assert e.value.code == -1
+        with pytest.raises(cw.CwslError):
+            rx.add_channel(g, -96001, 0.9)                  # SSBD.hpp:100
+        with pytest.raises(cw.CwslError):
+            rx.add_channel(g, 0, 1.5)                       # CWSL_DIGI.cpp:952-978
+        with pytest.raises(cw.CwslError):
+            rx.add_channel(g + 1, 0, 0.9)
+        rx.add_channel(g, 0, 0.9)
+        rx.push_iq(np.zeros(2048 * 2, np.float32))
+        with pytest.raises(cw.CwslError) as e:
+            rx.add_channel(g, 100, 0.9)                     # after the first push
+        assert e.value.code == -4
+
+
+def test_fp32_peak_probe(gpu):
+    p = gpu.measure_fp32_peak(0)
+    assert 20.0 < p["ffma2_tflops"] < 120.0
