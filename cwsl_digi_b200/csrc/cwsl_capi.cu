@@ -106,6 +106,8 @@ struct cwsl_rx {
     float2* d_ring = nullptr;        // owned ring (nullptr while bound to external IQ)
     const float2* ring_ptr = nullptr;  // what the kernels read
     uint32_t ring_blocks = 0;
+    uint32_t own_ring_blocks = 0;
+    uint64_t max_slot_blocks = 0;
     uint64_t abs_written = 0;  // SSBD blocks pushed since creation
     bool bound = false;
     bool committed = false;
@@ -258,22 +260,38 @@ int commit(cwsl_rx* rx) {
             cudaFree((void*)d_tab);
         }
     }
-    // IQ ring
-    if (!rx->bound) {
-        double secs = rx->ring_seconds;
+    rx->max_slot_blocks = max_blocks;
+    rx->committed = true;
+    return CWSL_OK;
+}
+
+// The receiver's own device ring, allocated on the first host/device push (a receiver that is only
+// ever bound to caller-resident IQ never needs one). Leaves "bound" mode: the next slot starts empty.
+int ensure_ring(cwsl_rx* rx) {
+    if (!rx->d_ring) {
+        const double secs = rx->ring_seconds;
         uint64_t blocks;
         if (secs > 0)
             blocks = (uint64_t)(secs * rx->fs / rx->geo.block_size);
         else
-            blocks = max_blocks + 64;  // longest slot (+5 s) fits without intermediate demodulation
+            blocks = rx->max_slot_blocks + 64;  // longest slot (+5 s) fits without intermediate demodulation
         const uint64_t quantum = std::max<uint64_t>(rx->sub, 4);
         blocks = std::max<uint64_t>(blocks, 4 * (uint64_t)rx->sub + 64);
         blocks = (blocks + quantum - 1) / quantum * quantum;
-        rx->ring_blocks = (uint32_t)blocks;
+        rx->own_ring_blocks = (uint32_t)blocks;
         CK(cudaMalloc(&rx->d_ring, (size_t)blocks * rx->geo.block_size * sizeof(float2)));
-        rx->ring_ptr = rx->d_ring;
     }
-    rx->committed = true;
+    if (rx->bound || rx->ring_ptr != rx->d_ring) {
+        rx->bound = false;
+        rx->ring_ptr = rx->d_ring;
+        rx->ring_blocks = rx->own_ring_blocks;
+        rx->abs_written = 0;
+        for (Group& g : rx->groups) {
+            g.slot_start = 0;
+            g.processed = 0;
+            g.iq_blocks = 0;
+        }
+    }
     return CWSL_OK;
 }
 
@@ -329,9 +347,9 @@ int push_common(cwsl_rx* rx, const float* iq, size_t n_blocks, cudaMemcpyKind ki
     if (!iq) return fail(CWSL_ERR_INVALID, "null IQ pointer");
     DeviceGuard dg(rx->device);
     if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
-    if (rx->bound) return fail(CWSL_ERR_STATE, "receiver is bound to an external IQ buffer");
     int rc = commit(rx);
     if (rc != CWSL_OK) return rc;
+    if ((rc = ensure_ring(rx)) != CWSL_OK) return rc;
     const uint32_t BS = rx->geo.block_size;
     // never let a single copy cover more than half the ring, so open slots can be drained first
     const size_t max_chunk = std::max<size_t>(1, (rx->ring_blocks / 2) / rx->sub);
@@ -569,13 +587,9 @@ int cwsl_rx_bind_device_iq(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks) {
     if ((reinterpret_cast<uintptr_t>(d_iq) & 15u) != 0) return fail(CWSL_ERR_INVALID, "IQ buffer must be 16-byte aligned");
     DeviceGuard dg(rx->device);
     if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
-    const bool was_bound = rx->bound;
-    rx->bound = true;
     int rc = commit(rx);
-    if (rc != CWSL_OK) {
-        rx->bound = was_bound;
-        return rc;
-    }
+    if (rc != CWSL_OK) return rc;
+    rx->bound = true;
     const uint64_t blocks = (uint64_t)n_blocks * rx->sub;
     if (blocks > 0xFFFFFFF0ull) return fail(CWSL_ERR_INVALID, "slot too long");
     rx->ring_ptr = reinterpret_cast<const float2*>(d_iq);

@@ -1,0 +1,150 @@
+// CPU-only unit tests of the host-side classes (no GPU call is made): decoder= grammar,
+// calibration arithmetic, mode/period table, WAV header bytes, DecoderPool hand-off, predicates.
+// Run by tests/test_host_cpu.py; exit code 0 = all passed.
+#include <cstdio>
+#include <cstdlib>
+#include <sstream>
+
+#include "cwsl_host.hpp"
+
+static int g_fail = 0;
+#define EXPECT(cond)                                                       \
+    do {                                                                   \
+        if (!(cond)) {                                                     \
+            std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            ++g_fail;                                                      \
+        }                                                                  \
+    } while (0)
+template <class F>
+static bool throws(F f) {
+    try {
+        f();
+    } catch (const std::exception&) {
+        return true;
+    }
+    return false;
+}
+
+int main(int argc, char** argv) {
+    const std::string tmp = argc > 1 ? argv[1] : "/tmp";
+
+    // ---- periods (source/CWSL_DIGI.hpp:64-113) ----
+    EXPECT(getRXPeriod("FT8") == 15.0f && getRXPeriod("FT4") == 7.5f && getRXPeriod("WSPR") == 120.0f);
+    EXPECT(getRXPeriod("JT65") == 60.0f && getRXPeriod("JS8") == 15.0f && getRXPeriod("Q65-30") == 30.0f);
+    EXPECT(getRXPeriod("FST4W-1800") == 1800.0f && getRXPeriod("FST4-300") == 300.0f);
+    EXPECT(throws([] { getRXPeriod("PSK31"); }));
+
+    // ---- decoder= grammar (source/CWSL_DIGI.cpp:731-842) ----
+    {
+        Decoder d = parseDecoderLine("14074000 FT8", 1.0, -1, "W1AW");
+        EXPECT(d.getFreq() == 14074000u && d.getFreqCalibrated() == 14074000u && d.getMode() == "FT8");
+        EXPECT(d.getsmNum() == -1 && d.getReporterCallsign() == "W1AW" && d.getTRPeriod() == 15.0f);
+        Decoder e = parseDecoderLine("14095600 WSPR 2 1.0000015 K1ABC", 1.00000071, -1, "W1AW");
+        EXPECT(e.getsmNum() == 2 && e.getReporterCallsign() == "K1ABC");
+        EXPECT(e.getFreqCalibrated() == static_cast<FrequencyHz>(14095600u / (1.00000071 * 1.0000015)));
+        EXPECT(e.getFreqCalibrated() == 14095568u);
+        EXPECT(throws([] { parseDecoderLine("14074000", 1.0, -1, ""); }));                    // 1 token
+        EXPECT(throws([] { parseDecoderLine("14074000 FT8 0 1.0 W1AW X", 1.0, -1, ""); }));    // 6 tokens
+        EXPECT(throws([] { parseDecoderLine("14074000 PSK31", 1.0, -1, ""); }));              // unknown mode
+        EXPECT(throws([] { parseDecoderLine("14074000 FT8 0 1.0 W1AW", 1.0, -1, ""); }));      // callsign on non-WSPR
+        EXPECT(throws([] { parseDecoderLine("14074000  FT8", 1.0, -1, ""); }));  // double space -> empty mode token
+    }
+    {
+        std::istringstream ini(
+            "[radio]\nfreqcalibration=1.0\nsharedmem=-1\n[operator]\ncallsign=N0CALL\n"
+            "[decoders]\n# 20m\ndecoder=14095600 WSPR\ndecoder=14074000 FT8\ndecoder=14080000 FT4\n"
+            "[wsjtx]\nftaudioscalefactor=0.85\n");
+        FrontEndConfig c = loadFrontEndConfig(ini);
+        EXPECT(c.decoders.size() == 3 && c.ftAudioScaleFactor == 0.85f && c.wsprAudioScaleFactor == 0.20f);
+        EXPECT(c.decoders[0].getReporterCallsign() == "N0CALL");
+        std::istringstream bad("[decoders]\ndecoder=14074000 FT8\n[wsjtx]\nftaudioscalefactor=1.5\n");
+        EXPECT(throws([&] { loadFrontEndConfig(bad); }));
+        std::istringstream none("[radio]\nfreqcalibration=1.0\n");
+        EXPECT(throws([&] { loadFrontEndConfig(none); }));
+    }
+
+    // ---- WAV hand-off (source/WaveFile.hpp:19-35; DecoderPool.hpp:915-964) ----
+    {
+        std::vector<std::int16_t> audio(240000);
+        for (size_t i = 0; i < audio.size(); ++i) audio[i] = static_cast<std::int16_t>(i * 7 - 1000);
+        const std::string path = tmp + "/cwsl_host_test.wav";
+        EXPECT(waveWrite(audio, path));
+        FILE* f = std::fopen(path.c_str(), "rb");
+        EXPECT(f != nullptr);
+        if (f) {
+            unsigned char h[46];
+            EXPECT(std::fread(h, 1, 46, f) == 46);
+            EXPECT(std::memcmp(h, "RIFF", 4) == 0 && std::memcmp(h + 8, "WAVEfmt ", 8) == 0);
+            auto u32 = [&](int o) { return h[o] | (h[o + 1] << 8) | (h[o + 2] << 16) | ((unsigned)h[o + 3] << 24); };
+            auto u16 = [&](int o) { return h[o] | (h[o + 1] << 8); };
+            EXPECT(u32(4) == 46 + 480000 - 8 && u32(16) == 18 && u16(20) == 1 && u16(22) == 1);
+            EXPECT(u32(24) == 12000 && u32(28) == 24000 && u16(32) == 2 && u16(34) == 16 && u16(36) == 0);
+            EXPECT(std::memcmp(h + 38, "data", 4) == 0 && u32(42) == 480000);
+            std::fseek(f, 0, SEEK_END);
+            EXPECT(std::ftell(f) == 46 + 480000);
+            std::int16_t s[2];
+            std::fseek(f, 46 + 2 * 1000, SEEK_SET);
+            EXPECT(std::fread(s, 2, 2, f) == 2 && s[0] == audio[1000] && s[1] == audio[1001]);
+            std::fclose(f);
+        }
+        std::remove(path.c_str());
+    }
+
+    // ---- DecoderPool: push -> worker -> WAV + sink; age check (source/DecoderPool.hpp:357-377) ----
+    {
+        auto sp = std::make_shared<ScreenPrinter>(LOG_LEVEL::ERR);
+        std::vector<std::string> seen;
+        std::mutex mu;
+        auto pool = std::make_shared<DecoderPool>("wavefile", tmp, 2, 300, sp,
+                                                  [&](const ItemToDecode& it, const std::string& path) {
+                                                      std::lock_guard<std::mutex> lk(mu);
+                                                      seen.push_back(it.mode + ":" + path);
+                                                      if (!path.empty()) std::remove(path.c_str());
+                                                  });
+        pool->init();
+        const std::uint64_t now = std::chrono::system_clock::now().time_since_epoch() / std::chrono::seconds(1);
+        for (int i = 0; i < 5; ++i)
+            pool->push(ItemToDecode(std::vector<std::int16_t>(150000, (std::int16_t)i), "FT4", now, 14080000, i, "cwd", 7.5f));
+        pool->push(ItemToDecode(std::vector<std::int16_t>(240000), "FT8", now - 10000, 14074000, 9, "cwd", 15.0f));  // stale
+        pool->drain();
+        pool->terminate();
+        EXPECT(seen.size() == 5 && pool->handled() == 5 && pool->droppedForAge() == 1);
+        for (auto& s : seen) EXPECT(s.rfind("FT4:", 0) == 0 && s.find(".wav") != std::string::npos);
+    }
+
+    // ---- predicates (source/CWSL_DIGI_Types.hpp:65-145) ----
+    {
+        SyncPredicates preds;
+        auto a = preds.createPredicate("FT8"), b = preds.createPredicate("FT8"), c = preds.createPredicate("JS8"),
+             d = preds.createPredicate("FT4");
+        EXPECT(a == b && a != c && !a->load());
+        preds.fire(15.0f);  // the 15 s clock thread fires FT8 and JS8 (source/CWSL_DIGI.cpp:234-262)
+        EXPECT(a->load() && c->load() && !d->load());
+        a->store(false);
+        EXPECT(!b->load());
+    }
+
+    // ---- Instance frequency plumbing without a GPU (source/Instance.cpp:183, :320-329) ----
+    {
+        auto sp = std::make_shared<ScreenPrinter>(LOG_LEVEL::ERR);
+        auto src = std::make_unique<SyntheticIqSource>(192000, 2048, 14100000, std::vector<SyntheticIqSource::Carrier>{});
+        auto rcv = std::make_shared<Receiver>("CWSL20Band0", sp, std::move(src));
+        // Receiver::init() needs a GPU; only the source side is exercised here
+        float blk[4096];
+        SyntheticIqSource s2(192000, 2048, 14100000, {{14075500.0, 8000.0}}, 300.0, 1, 2);
+        EXPECT(s2.readBlock(blk) && s2.readBlock(blk) && !s2.readBlock(blk));
+        auto pool = std::make_shared<DecoderPool>("none", tmp, 0, 300, sp);
+        auto pred = std::make_shared<SyncPredicate>();
+        Instance w(rcv, 0, pred, 14095600, 14095600, "WSPR", "N0CALL", 12000, 0.9f, 0.2f, sp, pool, 120.0f);
+        Instance f(rcv, 1, pred, 14097000, 14097000, "FST4W-120", "N0CALL", 12000, 0.9f, 0.2f, sp, pool, 120.0f);
+        EXPECT(w.audioScale() == 0.2f && f.audioScale() == 0.9f);
+        EXPECT(w.getStatus() == InstanceStatus::NOT_INITIALIZED);
+    }
+
+    if (g_fail) {
+        std::fprintf(stderr, "%d host test(s) failed\n", g_fail);
+        return 1;
+    }
+    std::printf("host tests ok\n");
+    return 0;
+}

@@ -316,7 +316,8 @@ def test_stress_properties(stress_run, ref):
     # zero tail and headroom: |q| <= 0.9*32767, tail all zero
     assert not base[:, wi:].any()
     assert np.abs(base.astype(np.int32)).max() <= int(0.9 * 32767) + 1
-    assert (np.abs(base.astype(np.int32)).max(axis=1) >= int(0.9 * 32767) - 2).all()
+    # every channel is normalised to 0.9*32767*max/(max+1): within 2 % of the ceiling for any real signal
+    assert (np.abs(base.astype(np.int32)).max(axis=1) >= int(0.98 * 0.9 * 32767)).all()
     # spot-check channels of the full-size run against the reference chain (fast-mode bars)
     iq = x.cpu().numpy()
     for c in (0, 511, 1023):
