@@ -111,7 +111,7 @@ private:
                 std::string path;
                 if (transferMethod == "wavefile") {
                     path = wavPath + "/" + std::to_string(item.epochTime) + "_" + std::to_string(item.baseFreq) + "_" +
-                           item.mode + "_" + std::to_string(item.instanceId) + ".wav";
+                           item.mode + "_" + std::to_string(item.instanceId) + "_" + std::to_string(nFiles++) + ".wav";
                     if (!waveWrite(item.audio, path)) {
                         screenPrinter->err("Error writing wave file data: " + path);
                         path.clear();
@@ -139,5 +139,5 @@ private:
     std::vector<std::thread> workers;
     std::atomic_bool terminateFlag{false};
     int busy = 0;
-    std::atomic<std::size_t> nHandled{0}, nDropped{0};
+    std::atomic<std::size_t> nHandled{0}, nDropped{0}, nFiles{0};  // nFiles: the reference names files by uuid (:901)
 };
