@@ -63,32 +63,36 @@ private:
     std::atomic_bool pred;
 };
 
-// One predicate per mode; every decoder of that mode shares it, which is what makes a mode a
-// "slot group" on the GPU (source/CWSL_DIGI_Types.hpp:80-145 keeps per-period vectors; the effect
-// -- all decoders of a period fire together -- is the same).
+// One predicate per decoder, kept in per-period lists; a clock thread sets every predicate of its
+// period at the slot edge (source/CWSL_DIGI_Types.hpp:80-145: ft8Preds holds FT8 and JS8, s60sPreds
+// JT65 and FST4-60, s120sPreds WSPR/FST4-120/FST4W-120, ...; source/CWSL_DIGI.cpp:234-262).
+// The decoders of one receiver that share a period form one "slot group" on the GPU.
 class SyncPredicates {
 public:
     std::shared_ptr<SyncPredicate> createPredicate(const std::string& mode) {
+        const float period = getRXPeriod(mode);  // throws "Unhandled mode" like the reference
+        std::shared_ptr<SyncPredicate> pred = std::make_shared<SyncPredicate>();
         std::lock_guard<std::mutex> lk(mu);
-        auto& p = byMode[mode];
-        if (!p) p = std::make_shared<SyncPredicate>();
-        return p;
+        byPeriod[period].push_back(pred);
+        return pred;
     }
-    // fire every mode whose period equals period_s (what one waitForTime* thread does)
+    // what one waitForTime* thread does at its slot edge: preds[k]->store(true) for all k
     void fire(float period_s) {
         std::lock_guard<std::mutex> lk(mu);
-        for (auto& kv : byMode)
-            if (std::fabs(getRXPeriod(kv.first) - period_s) < 1e-6f) kv.second->store(true);
+        auto it = byPeriod.find(period_s);
+        if (it == byPeriod.end()) return;
+        for (auto& p : it->second) p->store(true);
     }
-    void fireMode(const std::string& mode) {
+    std::vector<float> periods() {
         std::lock_guard<std::mutex> lk(mu);
-        auto it = byMode.find(mode);
-        if (it != byMode.end()) it->second->store(true);
+        std::vector<float> v;
+        for (auto& kv : byPeriod) v.push_back(kv.first);
+        return v;
     }
 
 private:
     std::mutex mu;
-    std::map<std::string, std::shared_ptr<SyncPredicate>> byMode;
+    std::map<float, std::vector<std::shared_ptr<SyncPredicate>>> byPeriod;
 };
 
 // Minimal levelled logger with the reference's method names (source/ScreenPrinter.hpp:37-45);

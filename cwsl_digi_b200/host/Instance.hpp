@@ -81,10 +81,9 @@ inline bool Receiver::addInstance(Instance* inst) {
     if (!rx || status == ReceiverStatus::RUNNING) return false;
     SlotGroup* g = nullptr;
     for (auto& sg : groups)
-        if (sg.pred == inst->getPredicate()) g = &sg;
+        if (sg.period == inst->getTRPeriod()) g = &sg;
     if (!g) {
         SlotGroup sg;
-        sg.pred = inst->getPredicate();
         sg.period = inst->getTRPeriod();
         sg.id = cwsl_rx_add_group(rx, sg.period);
         if (sg.id < 0) return false;
@@ -96,6 +95,7 @@ inline bool Receiver::addInstance(Instance* inst) {
     inst->group = g->id;
     inst->channel = ch;
     g->members.push_back(inst);
+    g->preds.push_back(inst->getPredicate());
     instances.push_back(inst);
     return true;
 }
@@ -132,8 +132,8 @@ inline void Receiver::readIQ() {
     while (!terminateFlag) {
         // slot edges first, like the Instance does at the top of its loop (Instance.cpp:203-206)
         for (auto& g : groups) {
-            if (g.pred->load()) {
-                g.pred->store(false);
+            if (g.preds.front()->load()) {
+                for (auto& p : g.preds) p->store(false);
                 finishSlot(g);
             }
         }

@@ -90,8 +90,11 @@ public:
     std::uint64_t slotsFinished() const { return nSlots.load(); }
 
 private:
+    // Decoders of this receiver that share a period = one GPU slot group. Every member keeps its own
+    // SyncPredicate like in the reference; the clock thread sets them in creation order, so the
+    // first member's flag is the group's edge and all members' flags are consumed together.
     struct SlotGroup {
-        std::shared_ptr<SyncPredicate> pred;
+        std::vector<std::shared_ptr<SyncPredicate>> preds;
         int id = -1;  // cwsl group id
         float period = 0;
         std::vector<Instance*> members;

@@ -116,12 +116,15 @@ int main(int argc, char** argv) {
     {
         SyncPredicates preds;
         auto a = preds.createPredicate("FT8"), b = preds.createPredicate("FT8"), c = preds.createPredicate("JS8"),
-             d = preds.createPredicate("FT4");
-        EXPECT(a == b && a != c && !a->load());
-        preds.fire(15.0f);  // the 15 s clock thread fires FT8 and JS8 (source/CWSL_DIGI.cpp:234-262)
-        EXPECT(a->load() && c->load() && !d->load());
+             d = preds.createPredicate("FT4"), w = preds.createPredicate("WSPR"), f = preds.createPredicate("FST4W-120");
+        EXPECT(a != b && !a->load());  // one predicate per decoder
+        preds.fire(15.0f);  // the 15 s clock thread fires FT8 and JS8 (ft8Preds, source/CWSL_DIGI.cpp:234-262)
+        EXPECT(a->load() && b->load() && c->load() && !d->load() && !w->load());
         a->store(false);
-        EXPECT(!b->load());
+        EXPECT(b->load());
+        preds.fire(120.0f);
+        EXPECT(w->load() && f->load() && !d->load());
+        EXPECT(throws([&] { preds.createPredicate("RTTY"); }));
     }
 
     // ---- Instance frequency plumbing without a GPU (source/Instance.cpp:183, :320-329) ----

@@ -73,7 +73,9 @@ int main(int argc, char** argv) {
 
     // one receiver per 192 kHz band segment (findBand(), source/CWSL_Utils.hpp:27-53, picks the CWSL
     // band containing the frequency; here bands are synthetic: LO = freq rounded to 100 kHz)
-    auto preds = std::make_shared<SyncPredicates>();
+    // signal time is simulated per receiver, so each receiver gets its own set of slot clocks
+    // (the reference has one wall clock for all, source/CWSL_DIGI.cpp:1134-1175)
+    std::map<FrequencyHz, std::shared_ptr<SyncPredicates>> preds;
     std::map<FrequencyHz, std::shared_ptr<Receiver>> receivers;
     std::map<FrequencyHz, std::set<float>> periods;
     std::map<FrequencyHz, std::vector<SyntheticIqSource::Carrier>> carriers;
@@ -88,8 +90,9 @@ int main(int argc, char** argv) {
     const std::uint64_t max_blocks = static_cast<std::uint64_t>(slots * longest * fs / iq_len) + 2;
     int ridx = 0;
     for (auto& kv : periods) {
+        preds[kv.first] = std::make_shared<SyncPredicates>();
         auto src = std::make_unique<ClockedSource>(fs, iq_len, kv.first, carriers[kv.first], 20261017 + ridx, max_blocks,
-                                                   preds, kv.second);
+                                                   preds[kv.first], kv.second);
         auto r = std::make_shared<Receiver>("SYNTH" + std::to_string(kv.first / 1000) + "kHz", printer, std::move(src),
                                             ridx % cwsl_device_count(), mode);
         if (!r->init()) return EXIT_FAILURE;
@@ -99,7 +102,7 @@ int main(int argc, char** argv) {
     std::size_t id = 0;
     for (auto& d : cfg.decoders) {  // setupDecoder(), source/CWSL_DIGI.cpp:103-172
         const FrequencyHz lo = (d.getFreqCalibrated() + 50000) / 100000 * 100000;
-        auto inst = std::make_unique<Instance>(receivers[lo], id++, preds->createPredicate(d.getMode()), d.getFreq(),
+        auto inst = std::make_unique<Instance>(receivers[lo], id++, preds[lo]->createPredicate(d.getMode()), d.getFreq(),
                                                d.getFreqCalibrated(), d.getMode(), d.getReporterCallsign(), Wave_SR,
                                                cfg.ftAudioScaleFactor, cfg.wsprAudioScaleFactor, printer, pool,
                                                d.getTRPeriod());
