@@ -210,7 +210,8 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     mode = cw.MODE_FAST if a.mode == "fast" else cw.MODE_EXACT
-    my_rx = list(range(rank, a.receivers, world))          # one receiver/band per GPU, round-robin
+    from cwsl_digi_b200.sharding import receivers_of_rank
+    my_rx = receivers_of_rank(a.receivers, rank, world)     # one receiver/band per GPU, round-robin
     n_blocks = int(PERIOD * FS) // IQ_LEN                   # 1406 IQ blocks = 2 879 488 samples
     n_iq = n_blocks * IQ_LEN
     freqs = synth.stress_demod_freqs(a.channels)
@@ -340,8 +341,8 @@ def run_b200(a):
         sample = torch.empty(afs, dtype=torch.int16, device="cuda")
         rxs[0].copy_device_audio(0, 0, sample.data_ptr())   # last slot, my first receiver, channel 0
         rxs[0].synchronize()
-        bucket = [torch.empty_like(sample) for _ in range(world)] if rank == 0 else None
-        dist.gather(sample, bucket, dst=0)
+        from cwsl_digi_b200.sharding import gather_slot_audio
+        bucket = gather_slot_audio(sample, dst=0)
         if rank == 0:
             gathered = [int(b.to(torch.int64).abs().sum().item()) for b in bucket]
 
