@@ -35,7 +35,13 @@ sys.path.insert(0, ROOT)
 
 FS, IQ_LEN, PERIOD = 192000, 2048, 15.0
 N_RECEIVERS, N_CHANNELS = 64, 1024
-FLOP_PER_CH_SAMPLE = 134.0          # SURVEY.md section 8d (mix 6 + 32 taps x 4)
+FLOP_PER_CH_SAMPLE = 134.0          # SURVEY.md section 8d (mix 6 + 32 taps x 4): the ALGORITHMIC work
+# What demod_fast_kernel<16,4,128> actually issues on the FMA pipe per SSBD block (16 ch-samples), from its SASS
+# (cuobjdump, 2x-unrolled loop: 514 FFMA2 + 156 FADD2 + 128 FMUL2 per 2 blocks): the symmetric taps are folded
+# (h[j] = h[512-j]) so fewer multiplies are executed than the algorithm counts. Each packed instruction = 2 lanes
+# x 2 flop-slots; tiles overlap by 32 of 512 blocks.
+FAST_PIPE_INSTR_PER_BLOCK = 399.0
+FAST_TILE_OVERHEAD = 512.0 / 480.0
 METRIC, UNIT = "channel-Msamples/s (IQ in x decoders)", "ch-Msamples/s"
 
 
@@ -373,7 +379,18 @@ def run_b200(a):
                                     "(cwsl_measure_fp32_peak); MEASURED_PEAKS.json has no FP32-pipe figure. "
                                     f"Nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; plain FFMA "
                                     f"measured {fp32['ffma_tflops']:.1f}",
-                        algorithmic="134 flop per channel-sample (SURVEY.md 8d) x channels x IQ samples per launch",
+                        algorithmic="134 flop per channel-sample (SURVEY.md 8d) x channels x IQ samples per launch; "
+                                    "frac can exceed 1: the kernel folds the symmetric taps and executes fewer "
+                                    "multiplies than the direct form the 134 counts (see 'executed')",
+                        executed=(dict(pipe_instr_per_block=FAST_PIPE_INSTR_PER_BLOCK,
+                                       flop_slots_per_ch_sample=FAST_PIPE_INSTR_PER_BLOCK * 4 / 16 * FAST_TILE_OVERHEAD,
+                                       tflops=FAST_PIPE_INSTR_PER_BLOCK * 4 / 16 * FAST_TILE_OVERHEAD * a.channels * n_iq
+                                       / (launch_ms * 1e-3) / 1e12,
+                                       frac_of_peak=FAST_PIPE_INSTR_PER_BLOCK * 4 / 16 * FAST_TILE_OVERHEAD * a.channels
+                                       * n_iq / (launch_ms * 1e-3) / 1e12 / peak_tf,
+                                       note="FMA-pipe lane-slots actually issued (packed f32x2 instr x 2 lanes x 2), "
+                                            "tile overlap included = FMA-pipe utilisation")
+                                  if a.mode == "fast" else None),
                         hbm=dict(achieved_gbs=bytes_per_launch / (launch_ms * 1e-3) / 1e9, peak_gbs=hbm_peak,
                                  frac=bytes_per_launch / (launch_ms * 1e-3) / 1e9 / hbm_peak,
                                  bytes_per_launch=bytes_per_launch, peak_source="MEASURED_PEAKS.json hbm_gbs"))

@@ -93,6 +93,11 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(as_u64(a)), "l"(as_u64(b)));
     return as_f2(d);
 }
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return as_f2(d);
+}
 __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }  // scalar broadcast operand
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -134,7 +139,7 @@ __device__ __forceinline__ void atomic_max_abs(unsigned* addr, float warp_local_
 
 // Compile-time copy of the taps with the FIR row update unrolled around them (FFMA2 immediates).
 template <int BS>
-struct FirRow;
+struct FirBlock;  // all 32 tap rows of one SSBD block (symmetric/folded form for BS >= 8)
 #include "cwsl_taps_baked.inc"
 
 const float* baked_taps_transposed(uint32_t block_size) {
@@ -272,7 +277,8 @@ struct FastCfg {
     static constexpr size_t kEBytes = (size_t)NT * kNE * 8;
     static constexpr size_t kOBytes = (size_t)NT * R * 8;
     static constexpr size_t kToneBytes = (size_t)kFastGMax * BS * 8;
-    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + 16;
+    static constexpr size_t kPtrBytes = (size_t)kFastGMax * 8;
+    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + kPtrBytes + 16;
 };
 
 template <int BS, int R, int NT>
@@ -284,7 +290,8 @@ __global__ void __launch_bounds__(NT, 2) demod_fast_kernel(DemodLaunch p, uint32
     float2* E = reinterpret_cast<float2*>(smem + Cfg::kXBytes);
     float2* O = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kEBytes);
     float4* tone_s = reinterpret_cast<float4*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes);
+    const float2** phase_s = reinterpret_cast<const float2**>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes + Cfg::kPtrBytes);
 
     const int t = threadIdx.x;
     const int64_t kt0 = (int64_t)p.b0 + (int64_t)blockIdx.x * Cfg::kTileOut - 32;
@@ -311,12 +318,23 @@ __global__ void __launch_bounds__(NT, 2) demod_fast_kernel(DemodLaunch p, uint32
     }
     for (uint32_t i = t; i < nch * (BS / 2); i += NT)
         tone_s[i] = reinterpret_cast<const float4*>(p.tone)[(size_t)c0 * (BS / 2) + i];
+    for (uint32_t i = t; i < nch; i += NT) phase_s[i] = p.phase[c0 + i];
     __syncthreads();
     mbar_wait(bar_a, 0);
 
     const float4* __restrict__ xrow = reinterpret_cast<const float4*>(xs + (size_t)t * Cfg::kRowStride);
     float2* __restrict__ Et = E + (size_t)t * Cfg::kNE;
-    float2* __restrict__ Ot = O + (size_t)t * R;
+
+    // phase values of my R blocks for the first channel; the next channel's are fetched while the
+    // current one is being computed (the table lives in HBM: ~1 us latency at 2 warps/SMSP)
+    float4 Pnext[R / 2];
+#pragma unroll
+    for (int i = 0; i < R / 2; ++i) Pnext[i] = make_float4(1.f, 0.f, 1.f, 0.f);
+    if (row_valid) {
+        const float4* pp = reinterpret_cast<const float4*>(phase_s[0] + kbase);
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
+    }
 
     for (uint32_t ci = 0; ci < nch; ++ci) {
         const uint32_t c = c0 + ci;
@@ -326,38 +344,48 @@ __global__ void __launch_bounds__(NT, 2) demod_fast_kernel(DemodLaunch p, uint32
         for (int o = 0; o < 32; ++o) acc[o] = make_float2(0.0f, 0.0f);
 
         if (row_valid) {
-            const float2* __restrict__ pp = p.phase[c] + kbase;
+            float4 Pcur[R / 2];
+#pragma unroll
+            for (int i = 0; i < R / 2; ++i) Pcur[i] = Pnext[i];
+            if (ci + 1 < nch) {
+                const float4* pp = reinterpret_cast<const float4*>(phase_s[ci + 1] + kbase);
+#pragma unroll
+                for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
+            }
             const float4* __restrict__ tn = tone_s + (size_t)ci * (BS / 2);
 #pragma unroll 1
             for (int r = 0; r < R; ++r) {
-                const float2 Pk = __ldg(pp + r);
+                float4 Pq = Pcur[0];
+#pragma unroll
+                for (int i = 1; i < R / 2; ++i) Pq = (r >> 1) == i ? Pcur[i] : Pq;
+                const float2 Pk = (r & 1) ? make_float2(Pq.z, Pq.w) : make_float2(Pq.x, Pq.y);
+                // mix: v[m] = x[m] * (tone[m] * P[k]); (a+ib)(c+id) = a*(c,d) + b*(-d,c)
+                float2 v[BS];
 #pragma unroll
                 for (int m2 = 0; m2 < BS / 2; ++m2) {
                     const float4 xx = xrow[r * (BS / 2) + m2];  // two IQ samples
                     const float4 tt = tn[m2];                  // their two tone entries
 #pragma unroll
                     for (int s = 0; s < 2; ++s) {
-                        const int m = 2 * m2 + s;
-                        // mix: v = x[m] * (tone[m] * P[k]); (a+ib)(c+id) = a*(c,d) + b*(-d,c)
                         const float2 tn_m = s ? make_float2(tt.z, tt.w) : make_float2(tt.x, tt.y);
                         float2 w = fmul2(tn_m, bc(Pk.x));
                         w = ffma2(make_float2(-tn_m.y, tn_m.x), bc(Pk.y), w);
                         const float xr = s ? xx.z : xx.x, xi = s ? xx.w : xx.y;
-                        float2 v = fmul2(w, bc(xr));
-                        v = ffma2(make_float2(-w.y, w.x), bc(xi), v);
-                        // FIR: tap row n of this block feeds output offset 31-n
-                        FirRow<BS>::apply(m, v, acc);
+                        float2 vv = fmul2(w, bc(xr));
+                        v[2 * m2 + s] = ffma2(make_float2(-w.y, w.x), bc(xi), vv);
                     }
                 }
+                // FIR: tap row n of this block feeds output offset 31-n
+                FirBlock<BS>::apply(v, acc);
                 // offset 0 is complete as far as this thread is concerned; slide the window
-                Ot[r] = acc[0];
+                O[r * NT + t] = acc[0];
 #pragma unroll
                 for (int o = 0; o < 31; ++o) acc[o] = acc[o + 1];
                 acc[31] = make_float2(0.0f, 0.0f);
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) Ot[r] = make_float2(0.0f, 0.0f);
+            for (int r = 0; r < R; ++r) O[r * NT + t] = make_float2(0.0f, 0.0f);
         }
 
         // ---- exchange partial sums: acc[0..30] are offsets R..R+30 ----
@@ -366,7 +394,7 @@ __global__ void __launch_bounds__(NT, 2) demod_fast_kernel(DemodLaunch p, uint32
         __syncthreads();
         float2 own[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) own[j] = Ot[j];
+        for (int j = 0; j < R; ++j) own[j] = O[j * NT + t];
 #pragma unroll
         for (int i = 1; i * R <= 30 + R; ++i) {
             if (t - i >= 0) {
