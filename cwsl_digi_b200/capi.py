@@ -18,7 +18,7 @@ SYMBOLS = [
     "cwsl_rx_group_af_size", "cwsl_rx_push_iq", "cwsl_rx_push_iq_device", "cwsl_rx_bind_device_iq",
     "cwsl_rx_process", "cwsl_rx_end_slot", "cwsl_rx_device_audio", "cwsl_rx_copy_device_audio", "cwsl_rx_read_float_audio",
     "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_stream", "cwsl_rx_set_stream", "cwsl_rx_enable_timing",
-    "cwsl_rx_kernel_times", "cwsl_measure_fp32_peak",
+    "cwsl_rx_kernel_times", "cwsl_measure_fp32_peak", "cwsl_host_alloc", "cwsl_host_free",
 ]
 
 
@@ -90,6 +90,10 @@ def lib() -> C.CDLL:
     L.cwsl_rx_enable_timing.argtypes = [vp, C.c_int]
     L.cwsl_rx_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int)]
+    L.cwsl_host_alloc.restype = vp
+    L.cwsl_host_alloc.argtypes = [sz]
+    L.cwsl_host_free.restype = None
+    L.cwsl_host_free.argtypes = [vp]
     L.cwsl_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = L
     return L
@@ -133,6 +137,27 @@ def measure_fp32_peak(device: int = 0) -> dict:
     a, b = C.c_float(), C.c_float()
     _check(lib().cwsl_measure_fp32_peak(device, C.byref(a), C.byref(b)))
     return dict(ffma_tflops=a.value, ffma2_tflops=b.value)
+
+
+class HostBuffer:
+    """Managed pinned hand-off buffer (cwsl_host_alloc) viewed as a numpy int16 array [rows, cols]."""
+
+    def __init__(self, rows: int, cols: int):
+        self._L = lib()
+        self.nbytes = rows * cols * 2
+        self.ptr = self._L.cwsl_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise CwslError(-3, self._L.cwsl_last_error().decode())
+        buf = (C.c_int16 * (rows * cols)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.int16).reshape(rows, cols)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self._L.cwsl_host_free(self.ptr)
+            self.ptr = None
+
+    __del__ = free
 
 
 class Receiver:

@@ -61,6 +61,19 @@ std::mutex g_mu;
 std::map<PhaseKey, PhaseEntry> g_phase_cache;
 std::set<std::pair<int, uint32_t>> g_taps_uploaded;
 
+// Managed hand-off buffers (cwsl_host_alloc): pinned, zero-initialised, and only ever written by
+// cwsl_rx_end_slot, so the library knows which columns of a destination can hold non-zero data and
+// copies only those (the zero tail of a slot buffer does not cross PCIe again).
+struct OutState {
+    size_t af_size = 0, rows = 0;
+    size_t dirty_cols = 0;  // columns [0, dirty_cols) of every row may be non-zero on the host
+};
+struct HostRegion {
+    size_t bytes = 0;
+    std::map<uintptr_t, OutState> outs;
+};
+std::map<uintptr_t, HostRegion> g_host_regions;  // base address -> region (guarded by g_mu)
+
 struct ChannelHost {
     int32_t demod_freq = 0;
     int usb = 1;
@@ -650,9 +663,40 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
         CK(cudaEventRecord(e1, rx->stream));
         rx->ev_quant.emplace_back(e0, e1);
     }
-    if (out_i16)
-        CK(cudaMemcpyAsync(out_i16, g->d_out, (size_t)C * g->af_size * sizeof(int16_t), cudaMemcpyDeviceToHost,
-                           rx->stream));
+    if (out_i16) {
+        size_t cols = g->af_size;  // default: the whole buffer, zero tail included
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            const uintptr_t a = reinterpret_cast<uintptr_t>(out_i16);
+            auto it = g_host_regions.upper_bound(a);
+            if (it != g_host_regions.begin()) {
+                --it;
+                const size_t need = (size_t)C * g->af_size * sizeof(int16_t);
+                if (a >= it->first && a + need <= it->first + it->second.bytes) {
+                    OutState& st = it->second.outs[a];
+                    if (st.af_size != g->af_size || st.rows != C) {
+                        // first use of this destination (or a different shape): drop overlapping records, the
+                        // region was zeroed at allocation so only what they wrote can be dirty -> full copy once
+                        const bool fresh = st.af_size == 0 && it->second.outs.size() == 1;
+                        if (!fresh)  // another destination in this region may overlap: nothing is known any more
+                            for (auto& kv : it->second.outs) kv.second.dirty_cols = kv.second.af_size;
+                        st.af_size = g->af_size;
+                        st.rows = C;
+                        st.dirty_cols = fresh ? 0 : g->af_size;
+                    }
+                    cols = std::max<size_t>(st.dirty_cols, (size_t)g->processed);
+                    st.dirty_cols = (size_t)g->processed;
+                }
+            }
+        }
+        if (cols >= g->af_size) {
+            CK(cudaMemcpyAsync(out_i16, g->d_out, (size_t)C * g->af_size * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                               rx->stream));
+        } else if (cols > 0) {
+            CK(cudaMemcpy2DAsync(out_i16, g->af_size * sizeof(int16_t), g->d_out, g->af_size * sizeof(int16_t),
+                                 cols * sizeof(int16_t), C, cudaMemcpyDeviceToHost, rx->stream));
+        }
+    }
     if (write_index) *write_index = (size_t)g->processed;
     g->last_write_index = (size_t)g->processed;
     g->have_result = true;
@@ -739,6 +783,32 @@ int cwsl_rx_kernel_times(cwsl_rx_t* rx, float* demod_ms, float* quant_ms, int* d
     rx->ev_demod.clear();
     rx->ev_quant.clear();
     return CWSL_OK;
+}
+
+void* cwsl_host_alloc(size_t bytes) {
+    if (bytes == 0) {
+        fail(CWSL_ERR_INVALID, "zero-size allocation");
+        return nullptr;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        fail(CWSL_ERR_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    std::memset(p, 0, bytes);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_host_regions[reinterpret_cast<uintptr_t>(p)].bytes = bytes;
+    return p;
+}
+
+void cwsl_host_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_host_regions.erase(reinterpret_cast<uintptr_t>(p));
+    }
+    cudaFreeHost(p);
 }
 
 int cwsl_measure_fp32_peak(int device, float* ffma_tflops, float* ffma2_tflops) {

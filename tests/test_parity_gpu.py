@@ -343,6 +343,29 @@ def test_stress_exact_spot_channels(stress_run, ref):
         assert np.array_equal(out[i], o["i16"])
 
 
+def test_managed_host_buffer_partial_copy(gpu, ref):
+    """cwsl_host_alloc buffers: only possibly-non-zero columns cross PCIe; result must equal the full copy,
+    including when a later slot is SHORTER than the previous one in the same buffer."""
+    cw = gpu
+    fs, iq_len = 192000, 2048
+    iq = synth.receiver_iq(60 * iq_len, fs, [-26000, 30000], receiver=6, tones_per_channel=2)
+    buf = cw.HostBuffer(2, af_size(15))
+    with cw.Receiver(0, fs, iq_len, mode=cw.MODE_EXACT) as rx:
+        g = rx.add_group(15.0)
+        rx.add_channel(g, -26000, 0.9)
+        rx.add_channel(g, 30000, 0.9)
+        for nblk in (40, 12, 25, 60):                 # long, shorter, longer, longest
+            span = iq[:nblk * iq_len * 2]
+            rx.push_iq(span)
+            wi = rx.end_slot(g, buf.ptr)
+            rx.synchronize()
+            for c, f in enumerate((-26000, 30000)):
+                o = ref.slot(fs, f, span, iq_len, 0.9, af_size(15))
+                assert wi == o["write_index"]
+                assert np.array_equal(buf.array[c], o["i16"]), (nblk, c)
+    buf.free()
+
+
 # ---- error behaviour mirrors the reference's exceptions / config checks --------------------------
 def test_error_behaviour(gpu):
     cw = gpu
