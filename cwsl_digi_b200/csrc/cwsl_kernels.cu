@@ -20,6 +20,7 @@
 //                        float audio store are fused in the epilogue.
 #include "cwsl_kernels.hpp"
 
+#include <algorithm>
 #include <cstdio>
 
 namespace cwsl {
@@ -253,205 +254,270 @@ cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
 // FAST demodulator.
 //
 // CTA = NT threads; thread t owns R consecutive SSBD blocks kbase = kt0 + t*R .. +R-1 ("row").
-// Rows are brought into shared memory by per-row TMA bulk copies (row stride padded by 16 B so
-// the per-thread LDS.128 of "my row" are bank-conflict free) and stay there while the CTA walks
-// its channels. Per channel every thread:
+// A CTA owns a time SEGMENT of `tiles_per_seg` tiles (tile = NT*R blocks) and a group of <= 32
+// channels. It walks the tiles forward in time; per tile the rows are brought into shared memory
+// by per-row TMA bulk copies (row stride padded by 16 B so the per-thread LDS.128 of "my row" are
+// bank-conflict free) and stay there while the CTA walks its channels. Per channel every thread:
 //   mixes its R blocks with w[m] = tone_c[m]*P_c[k] (packed complex multiply),
-//   accumulates acc[r+31-n] += v[m]*h[16n+m] for all 32 tap rows (FFMA2, tap = uniform-register
-//   broadcast) -> 31+R partial sums indexed by output offset,
-//   hands acc[R..30+R] to the R-aligned later threads through shared memory and finishes its own
-//   R outputs acc[0..R-1] with what the earlier threads handed over.
-// Tiles overlap by 32 blocks (the first 32/R threads only produce hand-over data), so every
-// (tile, channel group) CTA is independent.
+//   accumulates acc[31-n] += v[m]*h[16n+m] for all 32 tap rows (FirBlock: folded symmetric taps,
+//   FFMA2 with immediate taps) -> 31+R partial sums indexed by output offset,
+//   hands acc[R..30+R] to the later threads through shared memory and finishes its own R outputs
+//   with what the (<= 8) earlier threads handed over.
+// What the last 32/R threads of a tile owe to the NEXT tile's first 31 outputs is reduced to 31
+// partial sums per channel ("carry") kept in shared memory, so only the first tile of a segment
+// recomputes a 32-block overlap.
 // ------------------------------------------------------------------------------------------
-constexpr int kFastGMax = 32;  // channels walked per CTA (tone tables staged in smem)
+constexpr int kFastGMax = 32;  // channels walked per CTA (tone tables, phase pointers, carries staged in smem)
 
 template <int BS, int R, int NT>
 struct FastCfg {
     static constexpr int kRowBytes = R * BS * 8;
     static constexpr int kRowStride = kRowBytes + 16;
     static constexpr int kHaloT = 32 / R;
-    static constexpr int kTileOut = (NT - kHaloT) * R;
+    static constexpr int kTile = NT * R;  // blocks per tile
     static constexpr int kNE = 31;
     static constexpr size_t kXBytes = (size_t)NT * kRowStride;
     static constexpr size_t kEBytes = (size_t)NT * kNE * 8;
     static constexpr size_t kOBytes = (size_t)NT * R * 8;
     static constexpr size_t kToneBytes = (size_t)kFastGMax * BS * 8;
-    static constexpr size_t kPtrBytes = (size_t)kFastGMax * 8;
-    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + kPtrBytes + 16;
+    static constexpr size_t kCarryBytes = (size_t)kFastGMax * 31 * 8;
+    // 2 CTAs/SM need 2*(kSmem + 1 KB reserved) <= 228 KB: 115 472 B for <16,4,128>
+    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + kCarryBytes + 16;
 };
 
-template <int BS, int R, int NT>
-__global__ void __launch_bounds__(NT, 2) demod_fast_kernel(DemodLaunch p, uint32_t ch_per_cta) {
+template <int BS, int R, int NT, int CTAS>
+__global__ void __launch_bounds__(NT, CTAS)
+    demod_fast_kernel(DemodLaunch p, uint32_t ch_per_cta, uint32_t tiles_per_seg) {
     using Cfg = FastCfg<BS, R, NT>;
     static_assert(32 % R == 0 && (R == 2 || R == 4), "R must be 2 or 4");
+    static_assert(NT >= 32 && Cfg::kHaloT <= NT, "tile too small");
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* xs = smem;
     float2* E = reinterpret_cast<float2*>(smem + Cfg::kXBytes);
     float2* O = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kEBytes);
     float4* tone_s = reinterpret_cast<float4*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes);
-    const float2** phase_s = reinterpret_cast<const float2**>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes + Cfg::kPtrBytes);
+    float2* carry_s = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes +
+                                                Cfg::kCarryBytes);
 
     const int t = threadIdx.x;
-    const int64_t kt0 = (int64_t)p.b0 + (int64_t)blockIdx.x * Cfg::kTileOut - 32;
-    const int64_t kbase = kt0 + (int64_t)t * R;
-    const bool row_valid = kbase >= 0 && kbase + R <= (int64_t)p.b1;
     const uint32_t c0 = blockIdx.y * ch_per_cta;
     const uint32_t nch = min(ch_per_cta, p.n_channels - c0);
+    const float2* const* __restrict__ phase_g = p.phase + c0;  // per-channel phase-table pointers (L1-resident)
+    // segment: outputs [seg_b0, seg_b1); its first tile starts 32 blocks early (overlap, no output there)
+    const int64_t seg_out = (int64_t)tiles_per_seg * Cfg::kTile - 32;
+    const int64_t seg_b0 = (int64_t)p.b0 + (int64_t)blockIdx.x * seg_out;
+    const int64_t seg_b1 = min(seg_b0 + seg_out, (int64_t)p.b1);
 
-    // ---- stage this tile's IQ rows (TMA bulk copies, one per thread row) ----
     const uint32_t bar_a = smem_u32(bar);
     if (t == 0) {
         mbar_init(bar_a, 1);
         fence_mbar_init();
-        int64_t lo = kt0 >= 0 ? 0 : (-kt0 + R - 1) / R;
-        int64_t hi = ((int64_t)p.b1 - kt0) / R;
-        if (hi > NT) hi = NT;
-        const uint32_t rows = hi > lo ? (uint32_t)(hi - lo) : 0u;
-        mbar_arrive_expect_tx(bar_a, rows * Cfg::kRowBytes);
-    }
-    __syncthreads();
-    if (row_valid) {
-        const uint32_t row = (uint32_t)((p.ring_off + (uint64_t)kbase) % p.ring_blocks);
-        tma_bulk_g2s(smem_u32(xs + (size_t)t * Cfg::kRowStride), p.iq_ring + (size_t)row * BS, Cfg::kRowBytes, bar_a);
     }
     for (uint32_t i = t; i < nch * (BS / 2); i += NT)
         tone_s[i] = reinterpret_cast<const float4*>(p.tone)[(size_t)c0 * (BS / 2) + i];
-    for (uint32_t i = t; i < nch; i += NT) phase_s[i] = p.phase[c0 + i];
     __syncthreads();
-    mbar_wait(bar_a, 0);
 
     const float4* __restrict__ xrow = reinterpret_cast<const float4*>(xs + (size_t)t * Cfg::kRowStride);
     float2* __restrict__ Et = E + (size_t)t * Cfg::kNE;
 
-    // phase values of my R blocks for the first channel; the next channel's are fetched while the
-    // current one is being computed (the table lives in HBM: ~1 us latency at 2 warps/SMSP)
-    float4 Pnext[R / 2];
-#pragma unroll
-    for (int i = 0; i < R / 2; ++i) Pnext[i] = make_float4(1.f, 0.f, 1.f, 0.f);
-    if (row_valid) {
-        const float4* pp = reinterpret_cast<const float4*>(phase_s[0] + kbase);
-#pragma unroll
-        for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
-    }
+    for (uint32_t tile = 0; tile < tiles_per_seg; ++tile) {
+        const int64_t kt0 = seg_b0 - 32 + (int64_t)tile * Cfg::kTile;
+        if (kt0 + 32 >= seg_b1 && tile > 0) break;  // nothing left to output
+        const int64_t kbase = kt0 + (int64_t)t * R;
+        const bool row_valid = kbase >= 0 && kbase + R <= (int64_t)p.b1;
+        // threads whose outputs are written: inside the segment; the overlap rows of the first tile are not
+        const bool writes = row_valid && kbase >= seg_b0 && kbase < seg_b1;
+        const bool first_tile = tile == 0;
 
-    for (uint32_t ci = 0; ci < nch; ++ci) {
-        const uint32_t c = c0 + ci;
-        // acc[i] = partial sum for output offset (blocks done so far) + i
-        float2 acc[32];
-#pragma unroll
-        for (int o = 0; o < 32; ++o) acc[o] = make_float2(0.0f, 0.0f);
-
+        // ---- stage this tile's IQ rows (TMA bulk copies, one per thread row) ----
+        if (t == 0) {
+            int64_t lo = kt0 >= 0 ? 0 : (-kt0 + R - 1) / R;
+            int64_t hi = ((int64_t)p.b1 - kt0) / R;
+            if (hi > NT) hi = NT;
+            const uint32_t rows = hi > lo ? (uint32_t)(hi - lo) : 0u;
+            mbar_arrive_expect_tx(bar_a, rows * Cfg::kRowBytes);
+        }
         if (row_valid) {
-            float4 Pcur[R / 2];
+            const uint32_t row = (uint32_t)((p.ring_off + (uint64_t)kbase) % p.ring_blocks);
+            tma_bulk_g2s(smem_u32(xs + (size_t)t * Cfg::kRowStride), p.iq_ring + (size_t)row * BS, Cfg::kRowBytes,
+                         bar_a);
+        }
+        // phase values of my R blocks for the first channel (later channels are prefetched one ahead:
+        // the tables live in HBM, ~1 us away at 2 warps per scheduler)
+        float4 Pnext[R / 2];
 #pragma unroll
-            for (int i = 0; i < R / 2; ++i) Pcur[i] = Pnext[i];
-            if (ci + 1 < nch) {
-                const float4* pp = reinterpret_cast<const float4*>(phase_s[ci + 1] + kbase);
+        for (int i = 0; i < R / 2; ++i) Pnext[i] = make_float4(1.f, 0.f, 1.f, 0.f);
+        if (row_valid) {
+            const float4* pp = reinterpret_cast<const float4*>(phase_g[0] + kbase);
 #pragma unroll
-                for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
-            }
-            const float4* __restrict__ tn = tone_s + (size_t)ci * (BS / 2);
+            for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
+        }
+        mbar_wait(bar_a, tile & 1u);
+
+        for (uint32_t ci = 0; ci < nch; ++ci) {
+            const uint32_t c = c0 + ci;
+            // acc[i] = partial sum for output offset (blocks done so far) + i
+            float2 acc[32];
+#pragma unroll
+            for (int o = 0; o < 32; ++o) acc[o] = make_float2(0.0f, 0.0f);
+
+            if (row_valid) {
+                float4 Pcur[R / 2];
+#pragma unroll
+                for (int i = 0; i < R / 2; ++i) Pcur[i] = Pnext[i];
+                if (ci + 1 < nch) {
+                    const float4* pp = reinterpret_cast<const float4*>(phase_g[ci + 1] + kbase);
+#pragma unroll
+                    for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
+                }
+                const float4* __restrict__ tn = tone_s + (size_t)ci * (BS / 2);
 #pragma unroll 1
-            for (int r = 0; r < R; ++r) {
-                float4 Pq = Pcur[0];
+                for (int r = 0; r < R; ++r) {
+                    float4 Pq = Pcur[0];
 #pragma unroll
-                for (int i = 1; i < R / 2; ++i) Pq = (r >> 1) == i ? Pcur[i] : Pq;
-                const float2 Pk = (r & 1) ? make_float2(Pq.z, Pq.w) : make_float2(Pq.x, Pq.y);
-                // mix: v[m] = x[m] * (tone[m] * P[k]); (a+ib)(c+id) = a*(c,d) + b*(-d,c)
-                float2 v[BS];
+                    for (int i = 1; i < R / 2; ++i) Pq = (r >> 1) == i ? Pcur[i] : Pq;
+                    const float2 Pk = (r & 1) ? make_float2(Pq.z, Pq.w) : make_float2(Pq.x, Pq.y);
+                    // mix: v[m] = x[m] * (tone[m] * P[k]); (a+ib)(c+id) = a*(c,d) + b*(-d,c)
+                    float2 v[BS];
 #pragma unroll
-                for (int m2 = 0; m2 < BS / 2; ++m2) {
-                    const float4 xx = xrow[r * (BS / 2) + m2];  // two IQ samples
-                    const float4 tt = tn[m2];                  // their two tone entries
+                    for (int m2 = 0; m2 < BS / 2; ++m2) {
+                        const float4 xx = xrow[r * (BS / 2) + m2];  // two IQ samples
+                        const float4 tt = tn[m2];                  // their two tone entries
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        const float2 tn_m = s ? make_float2(tt.z, tt.w) : make_float2(tt.x, tt.y);
-                        float2 w = fmul2(tn_m, bc(Pk.x));
-                        w = ffma2(make_float2(-tn_m.y, tn_m.x), bc(Pk.y), w);
-                        const float xr = s ? xx.z : xx.x, xi = s ? xx.w : xx.y;
-                        float2 vv = fmul2(w, bc(xr));
-                        v[2 * m2 + s] = ffma2(make_float2(-w.y, w.x), bc(xi), vv);
+                        for (int s = 0; s < 2; ++s) {
+                            const float2 tn_m = s ? make_float2(tt.z, tt.w) : make_float2(tt.x, tt.y);
+                            float2 w = fmul2(tn_m, bc(Pk.x));
+                            w = ffma2(make_float2(-tn_m.y, tn_m.x), bc(Pk.y), w);
+                            const float xr = s ? xx.z : xx.x, xi = s ? xx.w : xx.y;
+                            float2 vv = fmul2(w, bc(xr));
+                            v[2 * m2 + s] = ffma2(make_float2(-w.y, w.x), bc(xi), vv);
+                        }
+                    }
+                    // FIR: tap row n of this block feeds output offset 31-n
+                    FirBlock<BS>::apply(v, acc);
+                    // offset 0 is complete as far as this thread is concerned; slide the window
+                    O[r * NT + t] = acc[0];
+#pragma unroll
+                    for (int o = 0; o < 31; ++o) acc[o] = acc[o + 1];
+                    acc[31] = make_float2(0.0f, 0.0f);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) O[r * NT + t] = make_float2(0.0f, 0.0f);
+            }
+
+            // ---- exchange partial sums: acc[0..30] are offsets R..R+30 ----
+#pragma unroll
+            for (int o = 0; o < 31; ++o) Et[o] = acc[o];
+            __syncthreads();
+            float2 own[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) own[j] = O[j * NT + t];
+#pragma unroll
+            for (int i = 1; i * R <= 30 + R; ++i) {
+                if (t - i >= 0) {
+                    const float2* __restrict__ Ei = E + (size_t)(t - i) * Cfg::kNE;
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const int o = j + i * R;
+                        if (o <= 30 + R) own[j] = fadd2(own[j], Ei[o - R]);
                     }
                 }
-                // FIR: tap row n of this block feeds output offset 31-n
-                FirBlock<BS>::apply(v, acc);
-                // offset 0 is complete as far as this thread is concerned; slide the window
-                O[r * NT + t] = acc[0];
-#pragma unroll
-                for (int o = 0; o < 31; ++o) acc[o] = acc[o + 1];
-                acc[31] = make_float2(0.0f, 0.0f);
             }
-        } else {
+            // what the previous tile owes to my outputs (first 31 output offsets of the tile)
+            if (!first_tile && t < Cfg::kHaloT) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) O[r * NT + t] = make_float2(0.0f, 0.0f);
-        }
+                for (int j = 0; j < R; ++j)
+                    if (t * R + j < 31) own[j] = fadd2(own[j], carry_s[ci * 31 + t * R + j]);
+            }
+            __syncwarp();
+            // what this tile owes to the next one: for output offset j' past the tile end, the hand-overs
+            // of the last threads that the (virtual) thread NT + j'/R would have collected
+            if (t < 31) {
+                const int q = t / R, j = t % R;
+                float2 cs = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int i = 1; i * R <= 30 + R; ++i) {
+                    const int o = j + i * R;
+                    if (i > q && o <= 30 + R) cs = fadd2(cs, E[(size_t)(NT + q - i) * Cfg::kNE + o - R]);
+                }
+                carry_s[ci * 31 + t] = cs;
+            }
 
-        // ---- exchange partial sums: acc[0..30] are offsets R..R+30 ----
-#pragma unroll
-        for (int o = 0; o < 31; ++o) Et[o] = acc[o];
-        __syncthreads();
-        float2 own[R];
-#pragma unroll
-        for (int j = 0; j < R; ++j) own[j] = O[j * NT + t];
-#pragma unroll
-        for (int i = 1; i * R <= 30 + R; ++i) {
-            if (t - i >= 0) {
-                const float2* __restrict__ Ei = E + (size_t)(t - i) * Cfg::kNE;
+            // ---- epilogue: Weaver select, float audio store, max|x| ----
+            float lmax = 0.0f;
+            if (writes) {
+                const float sign = p.sign[c];
+                float o4[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
-                    const int o = j + i * R;
-                    if (o <= 30 + R) own[j] = fadd2(own[j], Ei[o - R]);
+                    o4[j] = weaver(own[j].x, own[j].y, (uint32_t)(kbase + j), sign);
+                    lmax = fmaxf(lmax, fabsf(o4[j]));
                 }
+                float* dst = p.audio + (size_t)c * p.af_stride + kbase;
+                if constexpr (R == 4)
+                    *reinterpret_cast<float4*>(dst) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                else
+                    *reinterpret_cast<float2*>(dst) = make_float2(o4[0], o4[1]);
             }
+            atomic_max_abs(p.maxbits + c, lmax);
+            __syncthreads();  // E/O are rewritten by the next channel, the IQ rows by the next tile
         }
-
-        // ---- epilogue: Weaver select, float audio store, max|x| ----
-        float lmax = 0.0f;
-        if (row_valid && t >= Cfg::kHaloT && kbase >= (int64_t)p.b0) {
-            const float sign = p.sign[c];
-            float o4[R];
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                o4[j] = weaver(own[j].x, own[j].y, (uint32_t)(kbase + j), sign);
-                lmax = fmaxf(lmax, fabsf(o4[j]));
-            }
-            float* dst = p.audio + (size_t)c * p.af_stride + kbase;
-            if constexpr (R == 4)
-                *reinterpret_cast<float4*>(dst) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-            else
-                *reinterpret_cast<float2*>(dst) = make_float2(o4[0], o4[1]);
-        }
-        atomic_max_abs(p.maxbits + c, lmax);
-        __syncthreads();  // E/O are rewritten by the next channel
     }
 }
 
-template <int BS, int R, int NT>
+// Tiles per segment: trade the 32-block overlap paid once per segment against the tail of the last
+// wave of CTAs. Cost model in block units, minimised over L.
+static uint32_t choose_tiles_per_seg(uint32_t n_out, uint32_t tile, uint32_t ch_groups, uint32_t slots) {
+    uint32_t best_l = 1;
+    double best = 1e300;
+    const uint32_t max_l = std::max<uint32_t>(1, std::min<uint32_t>(64, (n_out + tile - 1) / tile + 1));
+    for (uint32_t l = 1; l <= max_l; ++l) {
+        const uint64_t seg_out = (uint64_t)l * tile - 32;
+        const uint64_t nseg = (n_out + seg_out - 1) / seg_out;
+        const uint64_t ctas = nseg * ch_groups;
+        const uint64_t waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * l * tile;  // every wave lasts as long as a full segment
+        if (cost < best * 0.999) {
+            best = cost;
+            best_l = l;
+        }
+    }
+    return best_l;
+}
+
+template <int BS, int R, int NT, int CTAS>
 static cudaError_t launch_fast_t(const DemodLaunch& p, cudaStream_t s) {
     using Cfg = FastCfg<BS, R, NT>;
     static bool attr_done = false;
-    auto kern = demod_fast_kernel<BS, R, NT>;
+    static int sms = 0;
+    auto kern = demod_fast_kernel<BS, R, NT, CTAS>;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
         if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
         attr_done = true;
     }
     const uint32_t n_out = p.b1 - p.b0;
-    const uint32_t tiles = (n_out + Cfg::kTileOut - 1) / Cfg::kTileOut;
-    uint32_t g = p.n_channels < (uint32_t)kFastGMax ? p.n_channels : (uint32_t)kFastGMax;
-    dim3 grid(tiles, (p.n_channels + g - 1) / g);
-    kern<<<grid, NT, Cfg::kSmem, s>>>(p, g);
+    const uint32_t g = p.n_channels < (uint32_t)kFastGMax ? p.n_channels : (uint32_t)kFastGMax;
+    const uint32_t groups = (p.n_channels + g - 1) / g;
+    const uint32_t l = choose_tiles_per_seg(n_out, Cfg::kTile, groups, (uint32_t)sms * CTAS);
+    const uint32_t seg_out = l * Cfg::kTile - 32;
+    dim3 grid((n_out + seg_out - 1) / seg_out, groups);
+    kern<<<grid, NT, Cfg::kSmem, s>>>(p, g, l);
     return cudaGetLastError();
 }
 
 cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s) {
     if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
     switch (p.block_size) {
-        case 16: return launch_fast_t<16, 4, 128>(p, s);
-        case 8: return launch_fast_t<8, 4, 128>(p, s);
-        case 4: return launch_fast_t<4, 4, 128>(p, s);
+        case 16: return launch_fast_t<16, 4, 128, 2>(p, s);
+        case 8: return launch_fast_t<8, 4, 128, 2>(p, s);
+        case 4: return launch_fast_t<4, 4, 128, 2>(p, s);
         default: return cudaErrorInvalidValue;
     }
 }
