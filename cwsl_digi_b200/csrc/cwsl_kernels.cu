@@ -395,11 +395,13 @@ __global__ void __launch_bounds__(NT, CTAS)
                         }
                     }
                     // FIR: tap row n of this block feeds output offset 31-n
-                    FirBlock<BS>::apply(v, acc);
+                    // (apply<true> would skip the adds onto known-zero accumulators of the first block, but
+                    // the extra control flow stops ptxas from unrolling this loop by two, which costs more)
+                    FirBlock<BS>::template apply<false>(v, acc);
                     // offset 0 is complete as far as this thread is concerned; slide the window
                     O[r * NT + t] = acc[0];
 #pragma unroll
-                    for (int o = 0; o < 31; ++o) acc[o] = acc[o + 1];
+                    for (int o = 0; o < 31; ++o) acc[o] = acc[o + 1];  // acc[31] is assigned by the next block
                     acc[31] = make_float2(0.0f, 0.0f);
                 }
             } else {
