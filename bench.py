@@ -37,11 +37,11 @@ FS, IQ_LEN, PERIOD = 192000, 2048, 15.0
 N_RECEIVERS, N_CHANNELS = 64, 1024
 FLOP_PER_CH_SAMPLE = 134.0          # SURVEY.md section 8d (mix 6 + 32 taps x 4): the ALGORITHMIC work
 # What demod_fast_kernel<16,4,128> actually issues on the FMA pipe per SSBD block (16 ch-samples), from its SASS
-# (cuobjdump, 2x-unrolled loop: 514 FFMA2 + 156 FADD2 + 128 FMUL2 per 2 blocks): the symmetric taps are folded
+# (cuobjdump, 2x-unrolled loop: 514 FFMA2 + 157 FADD2 + 128 FMUL2 per 2 blocks): the symmetric taps are folded
 # (h[j] = h[512-j]) so fewer multiplies are executed than the algorithm counts. Each packed instruction = 2 lanes
-# x 2 flop-slots; tiles overlap by 32 of 512 blocks.
-FAST_PIPE_INSTR_PER_BLOCK = 399.0
-FAST_TILE_OVERHEAD = 512.0 / 480.0
+# x 2 flop-slots; a segment of 3 tiles (1536 blocks) recomputes a 32-block overlap once.
+FAST_PIPE_INSTR_PER_BLOCK = 399.5
+FAST_TILE_OVERHEAD = 1536.0 / 1504.0
 METRIC, UNIT = "channel-Msamples/s (IQ in x decoders)", "ch-Msamples/s"
 
 
@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-station", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-time budget of the cpu_baseline leg")
     return ap.parse_args()
 
@@ -344,6 +345,11 @@ def run_b200(a):
                    note="pinned host IQ -> cwsl_rx_push_iq -> cwsl_rx_end_slot(host int16); timed region includes "
                         "every H2D and D2H copy; wall clock around a device synchronize, max over ranks")
 
+    # ---- BASELINE.json configs[2]: the 8-receiver x 7-mode skimmer station, streamed ----------------------
+    station = None
+    if not a.no_station:
+        station = run_station(cw, torch, dist, rank, world, local, mode)
+
     # ---- station-level gather (NCCL): rank 0 collects one channel's audio per rank ------------------------
     gathered = None
     if world > 1:
@@ -417,6 +423,7 @@ def run_b200(a):
                     gchs_per_gpu=value / 1e3 / world,
                     clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                     kernel_ms=dict(demod=demod_ms, quantise_and_clear=quant_ms, event_total=ms_total),
+                    station=station,
                     gathered_checksums=gathered)
         print(json.dumps(line), flush=True)
     for rx in rxs:
@@ -424,6 +431,77 @@ def run_b200(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+STATION_MODES = [("FT8", 15.0, 0.90), ("FT4", 7.5, 0.90), ("JT65", 60.0, 0.90), ("WSPR", 120.0, 0.20),
+                 ("FST4-120", 120.0, 0.90), ("FST4W-120", 120.0, 0.90), ("JS8", 15.0, 0.90)]
+
+
+def run_station(cw, torch, dist, rank, world, local, mode, n_receivers=8, hyper_s=120.0, chunk_s=1.5):
+    """8 receivers (bands) x 7 mode families = 56 decoders (README.md:3), receiver r on rank r mod world.
+    One 120 s hyper-period of signal per receiver is streamed from pinned HOST memory in 1.5 s pushes through
+    a 3 s device ring; every mode's slot ends on its own period boundary (8 FT8, 16 FT4, 2 JT65, 1 WSPR ...),
+    the int16 audio of each finished slot is copied back to the host. Reports x real time."""
+    from cwsl_digi_b200.sharding import receivers_of_rank
+    mine = receivers_of_rank(n_receivers, rank, world)
+    blocks_per_chunk = int(chunk_s * FS) // IQ_LEN            # 140 IQ blocks = 1.493 s
+    n_chunks = int(hyper_s / chunk_s)
+    n_blocks = blocks_per_chunk * n_chunks
+    rxs, hosts, outs, groups = [], [], [], []
+    for r in mine:
+        rx = cw.Receiver(local, FS, IQ_LEN, ring_seconds=3.0, mode=mode)
+        gmap = {}
+        for j, (name, per, sc) in enumerate(STATION_MODES):
+            if per not in gmap:
+                gmap[per] = rx.add_group(per)
+            rx.add_channel(gmap[per], -80000 + 20000 * j + 1000 * r, sc)
+        rxs.append(rx)
+        groups.append(gmap)
+        g = torch.Generator(device="cuda").manual_seed(777 + r)
+        x = torch.randn(2 * n_blocks * IQ_LEN, device="cuda", generator=g) * 300.0
+        h = torch.empty(2 * n_blocks * IQ_LEN, dtype=torch.float32).pin_memory()
+        h.copy_(x)
+        hosts.append(h)
+        outs.append({per: cw.HostBuffer(rx.num_channels(gi), rx.group_af_size(gi)) for per, gi in gmap.items()})
+        del x
+    torch.cuda.synchronize()
+
+    def one_pass():
+        slots = 0
+        for ck in range(n_chunks):
+            t_end = (ck + 1) * chunk_s
+            for rx, h, gmap, ob in zip(rxs, hosts, groups, outs):
+                rx.push_iq((h.data_ptr() + ck * blocks_per_chunk * IQ_LEN * 8, blocks_per_chunk))
+                for per, gi in gmap.items():
+                    if abs((t_end / per) - round(t_end / per)) < 1e-9:      # this mode's slot edge
+                        rx.end_slot(gi, ob[per].ptr)
+                        slots += 1
+        for rx in rxs:
+            rx.synchronize()
+        return slots
+
+    one_pass()                                                  # warm-up (allocations, first launches)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    slots = one_pass()
+    wall = time.perf_counter() - t0
+    tw = torch.tensor([wall], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    wall = float(tw.item())
+    for rx in rxs:
+        rx.close()
+    for ob in outs:
+        for b in ob.values():
+            b.free()
+    chs = float(n_receivers) * len(STATION_MODES) * n_blocks * IQ_LEN
+    return dict(workload="8 receivers x 7 modes = 56 decoders (BASELINE.json configs[2]), 120 s of signal per receiver "
+                         "streamed from pinned host memory in 1.5 s pushes through a 3 s device ring, slot edges per mode, "
+                         "int16 audio of every slot copied back to the host",
+                x_realtime=hyper_s / wall, wall_s=wall, value=chs / wall / 1e6, unit=UNIT,
+                receivers_per_rank=len(mine), slots_finished_per_rank=slots, mode="fast" if mode == 1 else "exact")
 
 
 def main():

@@ -9,3 +9,5 @@
 #include "Instance.hpp"
 #include "Decoder_impl.hpp"
 #include "Config.hpp"
+#include "SlotClock.hpp"
+#include "CwslSharedMemory.hpp"

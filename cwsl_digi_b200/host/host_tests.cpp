@@ -144,6 +144,61 @@ int main(int argc, char** argv) {
         EXPECT(w.getStatus() == InstanceStatus::NOT_INITIALIZED);
     }
 
+    // ---- wall-clock slot edges (source/CWSL_DIGI.cpp:174-451), with an injected clock ----
+    {
+        auto T = [](int m, int s, int ms) { UtcTime t; t.minute = m; t.second = s; t.millis = ms; return t; };
+        EXPECT(slotEdgeNow(15.0f, T(3, 15, 10)) && !slotEdgeNow(15.0f, T(3, 16, 0)) && slotEdgeNow(15.0f, T(3, 0, 999)));
+        EXPECT(slotEdgeNow(7.5f, T(0, 30, 0)) && !slotEdgeNow(7.5f, T(0, 7, 299)) && slotEdgeNow(7.5f, T(0, 7, 300)));
+        EXPECT(slotEdgeNow(7.5f, T(0, 52, 400)) && !slotEdgeNow(7.5f, T(0, 8, 0)));
+        EXPECT(slotEdgeNow(30.0f, T(9, 30, 0)) && !slotEdgeNow(30.0f, T(9, 15, 0)));
+        EXPECT(slotEdgeNow(60.0f, T(9, 0, 0)) && !slotEdgeNow(60.0f, T(9, 30, 0)));
+        EXPECT(slotEdgeNow(120.0f, T(10, 0, 0)) && !slotEdgeNow(120.0f, T(11, 0, 0)));
+        EXPECT(slotEdgeNow(300.0f, T(25, 0, 0)) && !slotEdgeNow(300.0f, T(26, 0, 0)));
+        EXPECT(slotEdgeNow(900.0f, T(45, 0, 0)) && !slotEdgeNow(900.0f, T(50, 0, 0)));
+        EXPECT(slotEdgeNow(1800.0f, T(30, 0, 0)) && !slotEdgeNow(1800.0f, T(15, 0, 0)));
+        // simulated two minutes polled every 25 ms: count the edges each period produces
+        auto preds = std::make_shared<SyncPredicates>();
+        auto p8 = preds->createPredicate("FT8"), p4 = preds->createPredicate("FT4"), pw = preds->createPredicate("WSPR"),
+             pj = preds->createPredicate("JT65");
+        std::uint64_t fake = 1792214520000ull;  // an even-minute boundary (divisible by 120000)
+        EXPECT(fake % 120000 == 0);
+        SlotClocks clk(preds, [&] { return fake; });
+        int l8 = -1, l4 = -1, lw = -1, lj = -1, n8 = 0, n4 = 0, nw = 0, nj = 0;
+        for (int i = 0; i < 120000 / 25; ++i, fake += 25) {
+            n8 += clk.poll(15.0f, l8);
+            n4 += clk.poll(7.5f, l4);
+            nw += clk.poll(120.0f, lw);
+            nj += clk.poll(60.0f, lj);
+        }
+        EXPECT(n8 == 8 && n4 == 16 && nw == 1 && nj == 2);
+        EXPECT(p8->load() && p4->load() && pw->load() && pj->load());
+    }
+
+    // ---- CWSL shared-memory layout on POSIX shm (source/SharedMemory.cpp:115-246) ----
+    {
+        const std::string name = createSharedMemName(7, -1) + "_t" + std::to_string(::getpid());
+        EXPECT(createSharedMemName(7, -1) == "CWSL7Band" && createSharedMemName(3, 2) == "CWSL3Band2");
+        CSharedMemory wr;
+        const std::uint32_t iq_len = 512, blk_bytes = iq_len * 8;
+        SM_HDR hdr{192000, (int)iq_len, 14100000};
+        EXPECT(wr.Create(name, blk_bytes * 5 + 24, hdr));   // ring not a multiple of the block: wrap splits a block
+        CwslShmSource src(200);
+        EXPECT(src.open(name));
+        EXPECT(src.sampleRate() == 192000 && src.blockInSamples() == iq_len && src.L0() == 14100000u);
+        std::vector<float> blk(iq_len * 2), got(iq_len * 2);
+        EXPECT(!src.readBlock(got.data()));                  // nothing written yet -> timeout
+        bool all = true;
+        for (int b = 0; b < 23; ++b) {
+            for (std::uint32_t i = 0; i < iq_len * 2; ++i) blk[i] = static_cast<float>(b * 10000 + (int)i);
+            EXPECT(wr.Write(reinterpret_cast<const std::uint8_t*>(blk.data()), blk_bytes));
+            EXPECT(src.readBlock(got.data()));
+            all = all && std::memcmp(blk.data(), got.data(), blk_bytes) == 0;
+        }
+        EXPECT(all);
+        CwslShmSource missing(50);
+        EXPECT(!missing.open("CWSL_no_such_band"));
+    }
+
     if (g_fail) {
         std::fprintf(stderr, "%d host test(s) failed\n", g_fail);
         return 1;

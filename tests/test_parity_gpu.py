@@ -267,6 +267,37 @@ def test_wspr_120s_exact(gpu, ref):
     assert np.array_equal(out[0], o["i16"])
 
 
+def test_fst4w_300s_long_slot(gpu, ref):
+    """BASELINE.json configs[3] (long-slot path): FST4W-300, 57.6 M IQ samples streamed through a 2 s device
+    ring in 1 s device-to-device pushes; 3.6 M phase-table steps; WSPR-style and FT-style scale factors."""
+    import torch
+    cw = gpu
+    fs, iq_len = 192000, 2048
+    nblk = 300 * fs // iq_len
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    x = torch.randn(nblk * iq_len * 2, device="cuda", generator=g) * 300.0
+    t = torch.arange(nblk * iq_len, device="cuda", dtype=torch.float64)
+    ph = 2 * np.pi * ((36000 + 1400) * t % fs) / fs
+    x[0::2] += (6000 * torch.cos(ph)).float()
+    x[1::2] += (6000 * torch.sin(ph)).float()
+    del t, ph
+    for mode, chk in ((cw.MODE_EXACT, check_exact), (cw.MODE_FAST, check_fast)):
+        with cw.Receiver(0, fs, iq_len, ring_seconds=2.0, mode=mode) as rx:
+            grp = rx.add_group(300.0)
+            rx.add_channel(grp, 36000, 0.90)
+            step = 93
+            for b in range(0, nblk, step):
+                rx.push_iq_device(x.data_ptr() + b * iq_len * 8, min(step, nblk - b))
+            out, wi = rx.end_slot_numpy(grp)
+            raw = rx.read_float_audio(grp, 0)[None]
+            stats = [rx.channel_stats(grp, 0)]
+        if mode == cw.MODE_EXACT:
+            iq = x.cpu().numpy()
+            o = ref.slot(fs, 36000, iq, iq_len, 0.90, af_size(300))
+            assert o["write_index"] == nblk * iq_len // 16 == wi
+        chk(out, raw, wi, stats, [o])
+
+
 # ---- properties at BASELINE's full size: 1024 channels x one FT8 slot, resident IQ ---------------
 @pytest.fixture(scope="module")
 def stress_run(gpu):
