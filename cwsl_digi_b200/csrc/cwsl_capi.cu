@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -342,8 +343,17 @@ int process_group(cwsl_rx* rx, Group& g) {
         e1 = get_event(rx);
         CK(cudaEventRecord(e0, rx->stream));
     }
-    if (rx->mode == CWSL_MODE_EXACT)
-        CK(cwsl::launch_demod_exact(p, rx->stream));
+    if (rx->mode == CWSL_MODE_EXACT) {
+        // CWSL_EXACT_KERNEL=gather selects the independent one-thread-per-output implementation (cross-check)
+        static const bool gather = [] {
+            const char* e = std::getenv("CWSL_EXACT_KERNEL");
+            return e && std::string(e) == "gather";
+        }();
+        if (gather)
+            CK(cwsl::launch_demod_exact_gather(p, rx->stream));
+        else
+            CK(cwsl::launch_demod_exact(p, rx->stream));
+    }
     else
         CK(cwsl::launch_demod_fast(p, rx->stream));
     if (rx->timing) {

@@ -100,6 +100,12 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
     return as_f2(d);
 }
 __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }  // scalar broadcast operand
+// EXACT-mode add of a packed product: ptxas 12.9 contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2
+// (even with -fmad=false; only scalar mul.rn/add.rn are left alone), so the add after a packed multiply is
+// issued as two scalar add.rn.f32. Same FMA-pipe time (a packed op occupies the pipe for two cycles).
+__device__ __forceinline__ float2 add_unfused(float2 a, float2 prod) {
+    return make_float2(__fadd_rn(a.x, prod.x), __fadd_rn(a.y, prod.y));
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -140,7 +146,9 @@ __device__ __forceinline__ void atomic_max_abs(unsigned* addr, float warp_local_
 
 // Compile-time copy of the taps with the FIR row update unrolled around them (FFMA2 immediates).
 template <int BS>
-struct FirBlock;  // all 32 tap rows of one SSBD block (symmetric/folded form for BS >= 8)
+struct FirBlock;   // all 32 tap rows of one SSBD block (symmetric/folded form for BS >= 8), FAST mode
+template <int BS>
+struct ExactRows;  // 8 tap rows at a time, unfused mul/add in the reference's order, EXACT mode
 #include "cwsl_taps_baked.inc"
 
 const float* baked_taps_transposed(uint32_t block_size) {
@@ -236,18 +244,6 @@ __global__ void __launch_bounds__(128) demod_exact_kernel(DemodLaunch p) {
         p.audio[(size_t)c * p.af_stride + b] = out;
     }
     atomic_max_abs(p.maxbits + c, live ? fabsf(out) : 0.0f);
-}
-
-cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
-    if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
-    dim3 grid((p.b1 - p.b0 + 127) / 128, p.n_channels);
-    switch (p.block_size) {
-        case 16: demod_exact_kernel<16><<<grid, 128, 0, s>>>(p); break;
-        case 8: demod_exact_kernel<8><<<grid, 128, 0, s>>>(p); break;
-        case 4: demod_exact_kernel<4><<<grid, 128, 0, s>>>(p); break;
-        default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -471,12 +467,13 @@ __global__ void __launch_bounds__(NT, CTAS)
 
 // Tiles per segment: trade the 32-block overlap paid once per segment against the tail of the last
 // wave of CTAs. Cost model in block units, minimised over L.
-static uint32_t choose_tiles_per_seg(uint32_t n_out, uint32_t tile, uint32_t ch_groups, uint32_t slots) {
+static uint32_t choose_tiles_per_seg(uint32_t n_out, uint32_t tile, uint32_t ch_groups, uint32_t slots,
+                                     uint32_t overlap = 32) {
     uint32_t best_l = 1;
     double best = 1e300;
     const uint32_t max_l = std::max<uint32_t>(1, std::min<uint32_t>(64, (n_out + tile - 1) / tile + 1));
     for (uint32_t l = 1; l <= max_l; ++l) {
-        const uint64_t seg_out = (uint64_t)l * tile - 32;
+        const uint64_t seg_out = (uint64_t)l * tile - overlap;
         const uint64_t nseg = (n_out + seg_out - 1) / seg_out;
         const uint64_t ctas = nseg * ch_groups;
         const uint64_t waves = (ctas + slots - 1) / slots;
@@ -487,6 +484,202 @@ static uint32_t choose_tiles_per_seg(uint32_t n_out, uint32_t tile, uint32_t ch_
         }
     }
     return best_l;
+}
+
+// ------------------------------------------------------------------------------------------
+// EXACT demodulator, production form ("scatter"): the reference's own loop structure
+// (source/SSBD.hpp:160-183) with one thread per SSBD block.
+//   thread k: v[m] = in[m]*tone[m]                    (unfused complex multiply)
+//             S[n] = sum_m v[m]*h[16n+m], m ascending (mul.rn.f32x2 + add.rn.f32x2, never contracted)
+//             D[k][n] = S[n]*phase_k                  (unfused complex multiply)
+//   thread b: y[b] = sum_{n ascending} D[b-31+n][n]   starting from +0
+// which is exactly the order in which the reference's circular workspace receives its terms, so the
+// result is bit-identical. Packed f32x2 instructions are two independent IEEE operations (re, im).
+// The CTA walks its tiles forward in time; the ascending-n prefix sums that the last 31 blocks of
+// a tile owe to the next tile's first 31 outputs are carried in shared memory (a prefix of the same
+// ordered sum, hence still bit-identical).
+// ------------------------------------------------------------------------------------------
+constexpr int kExactGMax = 24;  // channels per CTA: keeps 2 CTAs (16 warps) per SM within 228 KB of shared memory
+
+template <int BS, int NT>
+struct ExactCfg {
+    static constexpr int kRowBytes = BS * 8;
+    static constexpr int kRowStride = kRowBytes + 16;   // conflict-free per-thread LDS.128
+    static constexpr int kDStride = 33;                 // float2 per D row (32 + 1 pad: conflict-free both ways)
+    static constexpr size_t kXBytes = (size_t)NT * kRowStride;
+    static constexpr size_t kDBytes = (size_t)NT * kDStride * 8;
+    static constexpr size_t kToneBytes = (size_t)kExactGMax * BS * 8;
+    static constexpr size_t kCarryBytes = (size_t)kExactGMax * 31 * 8;
+    static constexpr size_t kSmem = kXBytes + kDBytes + kToneBytes + kCarryBytes + 16;
+};
+
+// (a + ib)(c + id) = (ac - bd, ad + bc), every product and the add/sub rounded separately: libstdc++'s
+// complex multiply as compiled with -ffp-contract=off
+__device__ __forceinline__ float2 cmul_unfused(float2 x, float2 y) {
+    const float2 p = fmul2(y, bc(x.x));                      // (a*c, a*d)
+    const float2 q = fmul2(make_float2(y.y, y.x), bc(x.y));  // (b*d, b*c)
+    return make_float2(__fsub_rn(p.x, q.x), __fadd_rn(p.y, q.y));  // (ac - bd, ad + bc), scalar: see add_unfused
+}
+
+template <int BS, int NT>
+__global__ void __launch_bounds__(NT, 2)
+    demod_exact_tiled_kernel(DemodLaunch p, uint32_t ch_per_cta, uint32_t tiles_per_seg) {
+    using Cfg = ExactCfg<BS, NT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* xs = smem;
+    float2* D = reinterpret_cast<float2*>(smem + Cfg::kXBytes);
+    float2* tone_s = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kDBytes);
+    float2* carry_s = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kDBytes + Cfg::kToneBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kDBytes + Cfg::kToneBytes + Cfg::kCarryBytes);
+
+    const int t = threadIdx.x;
+    const uint32_t c0 = blockIdx.y * ch_per_cta;
+    const uint32_t nch = min(ch_per_cta, p.n_channels - c0);
+    const float2* const* __restrict__ phase_g = p.phase + c0;
+    // segment of outputs [seg_b0, seg_b1); its first tile starts 31 blocks early (history, no output)
+    const int64_t seg_out = (int64_t)tiles_per_seg * NT - 31;
+    const int64_t seg_b0 = (int64_t)p.b0 + (int64_t)blockIdx.x * seg_out;
+    const int64_t seg_b1 = min(seg_b0 + seg_out, (int64_t)p.b1);
+
+    const uint32_t bar_a = smem_u32(bar);
+    if (t == 0) {
+        mbar_init(bar_a, 1);
+        fence_mbar_init();
+    }
+    for (uint32_t i = t; i < nch * BS; i += NT) tone_s[i] = p.tone[(size_t)c0 * BS + i];
+    __syncthreads();
+
+    const float4* __restrict__ xrow = reinterpret_cast<const float4*>(xs + (size_t)t * Cfg::kRowStride);
+    float2* __restrict__ Dt = D + (size_t)t * Cfg::kDStride;
+
+    for (uint32_t tile = 0; tile < tiles_per_seg; ++tile) {
+        const int64_t kt0 = seg_b0 - 31 + (int64_t)tile * NT;
+        if (kt0 + 31 >= seg_b1 && tile > 0) break;
+        const int64_t k = kt0 + t;  // my block = my output
+        const bool row_valid = k >= 0 && k < (int64_t)p.b1;
+        const bool writes = row_valid && k >= seg_b0 && k < seg_b1;
+        const bool first_tile = tile == 0;
+
+        if (t == 0) {
+            const int64_t lo = kt0 >= 0 ? 0 : -kt0;
+            int64_t hi = (int64_t)p.b1 - kt0;
+            if (hi > NT) hi = NT;
+            const uint32_t rows = hi > lo ? (uint32_t)(hi - lo) : 0u;
+            mbar_arrive_expect_tx(bar_a, rows * Cfg::kRowBytes);
+        }
+        if (row_valid) {
+            const uint32_t row = (uint32_t)((p.ring_off + (uint64_t)k) % p.ring_blocks);
+            tma_bulk_g2s(smem_u32(xs + (size_t)t * Cfg::kRowStride), p.iq_ring + (size_t)row * BS, Cfg::kRowBytes, bar_a);
+        }
+        float2 Pnext = make_float2(1.0f, 0.0f);
+        if (row_valid) Pnext = __ldg(phase_g[0] + k);
+        mbar_wait(bar_a, tile & 1u);
+
+        for (uint32_t ci = 0; ci < nch; ++ci) {
+            const uint32_t c = c0 + ci;
+            if (row_valid) {
+                const float2 Pk = Pnext;
+                if (ci + 1 < nch) Pnext = __ldg(phase_g[ci + 1] + k);
+                const float2* __restrict__ tn = tone_s + (size_t)ci * BS;
+                float2 v[BS];
+#pragma unroll
+                for (int m2 = 0; m2 < BS / 2; ++m2) {
+                    const float4 xx = xrow[m2];
+                    v[2 * m2] = cmul_unfused(make_float2(xx.x, xx.y), tn[2 * m2]);          // in[m]*tone[m]
+                    v[2 * m2 + 1] = cmul_unfused(make_float2(xx.z, xx.w), tn[2 * m2 + 1]);
+                }
+                float2 S[8];
+                ExactRows<BS>::template apply<0>(v, S);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Dt[i] = cmul_unfused(S[i], Pk);                   // sum*phase
+                ExactRows<BS>::template apply<1>(v, S);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Dt[8 + i] = cmul_unfused(S[i], Pk);
+                ExactRows<BS>::template apply<2>(v, S);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Dt[16 + i] = cmul_unfused(S[i], Pk);
+                ExactRows<BS>::template apply<3>(v, S);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Dt[24 + i] = cmul_unfused(S[i], Pk);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) Dt[i] = make_float2(0.0f, 0.0f);
+            }
+            __syncthreads();
+
+            // y[b] = sum over tap rows n ascending of D[b-31+n][n]; rows before this tile are in the carry
+            float2 w = make_float2(0.0f, 0.0f);
+            if (!first_tile && t < 31) w = carry_s[ci * 31 + t];
+            // a row that is outside the slot (k < 0: fresh-SSBD history) is never added by the reference, so it
+            // must not be added here either (adding +0 could flip a -0): rows < 0 only occur in the first tile
+            const int n_lo = max(0, 31 - t);  // first tap row whose source block lies in this tile
+#pragma unroll
+            for (int n = 0; n < 32; ++n) {
+                if (n >= n_lo) {
+                    const int64_t src_k = kt0 + t - 31 + n;
+                    if (src_k >= 0) w = fadd2(w, D[(size_t)(t - 31 + n) * Cfg::kDStride + n]);
+                }
+            }
+            __syncwarp();
+            // prefix owed to the next tile: output NT + j gets rows (NT + j - 31 + n) < NT, n ascending
+            if (t < 31) {
+                float2 cs = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int n = 0; n < 31; ++n) {
+                    const int src = NT + t - 31 + n;  // tile-local row
+                    if (src < NT && kt0 + src >= 0) cs = fadd2(cs, D[(size_t)src * Cfg::kDStride + n]);
+                }
+                carry_s[ci * 31 + t] = cs;
+            }
+
+            float out = 0.0f;
+            if (writes) {
+                out = weaver(w.x, w.y, (uint32_t)k, p.sign[c]);
+                p.audio[(size_t)c * p.af_stride + k] = out;
+            }
+            atomic_max_abs(p.maxbits + c, writes ? fabsf(out) : 0.0f);
+            __syncthreads();
+        }
+    }
+}
+
+template <int BS, int NT>
+static cudaError_t launch_exact_t(const DemodLaunch& p, cudaStream_t s) {
+    using Cfg = ExactCfg<BS, NT>;
+    static bool attr_done = false;
+    static int sms = 0;
+    auto kern = demod_exact_tiled_kernel<BS, NT>;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+        attr_done = true;
+    }
+    const uint32_t n_out = p.b1 - p.b0;
+    const uint32_t g = p.n_channels < (uint32_t)kExactGMax ? p.n_channels : (uint32_t)kExactGMax;
+    const uint32_t groups = (p.n_channels + g - 1) / g;
+    const uint32_t l = choose_tiles_per_seg(n_out, NT, groups, (uint32_t)sms * 2, 31);
+    const uint32_t seg_out = l * NT - 31;
+    dim3 grid((n_out + seg_out - 1) / seg_out, groups);
+    kern<<<grid, NT, Cfg::kSmem, s>>>(p, g, l);
+    return cudaGetLastError();
+}
+
+// The one-thread-per-output gather kernel above is kept as an independent second implementation
+// (tests run both against the oracle); production EXACT mode uses the tiled kernel.
+cudaError_t launch_demod_exact_gather(const DemodLaunch& p, cudaStream_t s) {
+    if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
+    dim3 grid((p.b1 - p.b0 + 127) / 128, p.n_channels);
+    switch (p.block_size) {
+        case 16: demod_exact_kernel<16><<<grid, 128, 0, s>>>(p); break;
+        case 8: demod_exact_kernel<8><<<grid, 128, 0, s>>>(p); break;
+        case 4: demod_exact_kernel<4><<<grid, 128, 0, s>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
 }
 
 template <int BS, int R, int NT, int CTAS>
@@ -512,6 +705,16 @@ static cudaError_t launch_fast_t(const DemodLaunch& p, cudaStream_t s) {
     dim3 grid((n_out + seg_out - 1) / seg_out, groups);
     kern<<<grid, NT, Cfg::kSmem, s>>>(p, g, l);
     return cudaGetLastError();
+}
+
+cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
+    if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
+    switch (p.block_size) {
+        case 16: return launch_exact_t<16, 256>(p, s);
+        case 8: return launch_exact_t<8, 256>(p, s);
+        case 4: return launch_exact_t<4, 256>(p, s);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s) {

@@ -50,7 +50,8 @@ const float* baked_taps_transposed(uint32_t block_size);
 cudaError_t launch_phase_tables(const float2* phase_inc /*[n]*/, float2* const* tables /*[n]*/, uint32_t n,
                                 uint32_t length, cudaStream_t s);
 
-cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s);
+cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s);         // tiled, production
+cudaError_t launch_demod_exact_gather(const DemodLaunch& p, cudaStream_t s);  // one thread per output, cross-check
 cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s);
 cudaError_t launch_quantise(const QuantLaunch& p, cudaStream_t s);
 cudaError_t launch_clear_u32(unsigned* p, uint32_t n, cudaStream_t s);

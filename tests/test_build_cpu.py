@@ -1,0 +1,55 @@
+"""CPU checks on the compiled sm_100a code (cuobjdump -sass): the EXACT kernels must contain no fused
+multiply-add (ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would silently break
+bit-exactness), the FAST kernel must be built from FFMA2 with TMA bulk copies (UBLKCP) and no local-memory spills."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+
+def _sass(cw):
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-sass", cw.lib_path()], capture_output=True, text=True, check=True).stdout
+    funcs = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+            funcs[name].append(line.split("*/", 1)[1].strip())
+    return funcs
+
+
+def _ops(body):
+    return [ins.split()[1].split(".")[0] if ins.startswith("@") else ins.split()[0].split(".")[0] for ins in body if ins]
+
+
+def test_exact_kernels_have_no_fused_multiply_add(cw):
+    funcs = _sass(cw)
+    # (quantise_kernel legitimately contains FFMA: it is the Newton iteration inside the IEEE-rounded __fdiv_rn)
+    exact = {k: v for k, v in funcs.items() if "demod_exact" in k or "phase_table" in k}
+    assert len(exact) >= 7
+    for name, body in exact.items():
+        ops = _ops(body)
+        assert "FFMA" not in ops and "FFMA2" not in ops, f"{name} contains a fused multiply-add"
+        assert "FMUL" in ops or "FMUL2" in ops
+
+
+def test_fast_kernel_is_ffma2_tma_and_spill_free(cw):
+    funcs = _sass(cw)
+    fast = {k: v for k, v in funcs.items() if "demod_fast_kernelILi16" in k}
+    assert len(fast) == 1
+    (name, body), = fast.items()
+    ops = _ops(body)
+    assert ops.count("FFMA2") > 400                     # packed FP32 FMA (Blackwell)
+    assert "UBLKCP" in ops                              # cp.async.bulk = TMA bulk copy engine
+    assert any(o.startswith("SYNCS") for o in ops)      # mbarrier
+    assert "LDL" not in ops and "STL" not in ops        # no register spills
+    imm = [ins for ins in body if ins.startswith("FFMA2") and re.search(r", -?[0-9]\.[0-9e+-]+, ", ins)]
+    assert len(imm) > 300                               # taps are FFMA2 immediates: no loads in the inner product
+    tiled = [v for k, v in funcs.items() if "demod_exact_tiled_kernelILi16" in k][0]
+    assert "UBLKCP" in _ops(tiled)
