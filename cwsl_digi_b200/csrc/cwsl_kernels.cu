@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace cwsl {
 
@@ -469,6 +470,13 @@ __global__ void __launch_bounds__(NT, CTAS)
 // wave of CTAs. Cost model in block units, minimised over L.
 static uint32_t choose_tiles_per_seg(uint32_t n_out, uint32_t tile, uint32_t ch_groups, uint32_t slots,
                                      uint32_t overlap = 32) {
+    // CWSL_TILES_PER_SEG=<n> pins the segment length (tests and compute-sanitizer runs use it to force the
+    // cross-tile carry path on small inputs)
+    static const uint32_t forced = [] {
+        const char* e = std::getenv("CWSL_TILES_PER_SEG");
+        return e ? (uint32_t)std::strtoul(e, nullptr, 10) : 0u;
+    }();
+    if (forced > 0) return forced;
     uint32_t best_l = 1;
     double best = 1e300;
     const uint32_t max_l = std::max<uint32_t>(1, std::min<uint32_t>(64, (n_out + tile - 1) / tile + 1));

@@ -374,6 +374,33 @@ def test_stress_exact_spot_channels(stress_run, ref):
         assert np.array_equal(out[i], o["i16"])
 
 
+@pytest.mark.parametrize("tiles", ["2", "5"])
+def test_forced_cross_tile_carry(gpu, tiles):
+    """Both kernels with the segment length pinned (CWSL_TILES_PER_SEG) so that the cross-tile carry path runs
+    on a small input; checked against the committed golden vectors in a subprocess (the knob is read once)."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, glob, sys; sys.path.insert(0, '.')\n"
+        "import cwsl_digi_b200 as cw\n"
+        "for path in sorted(glob.glob('tests/golden/*.npz')):\n"
+        "    g = np.load(path)\n"
+        "    for mode in (cw.MODE_EXACT, cw.MODE_FAST):\n"
+        "        with cw.Receiver(0, int(g['fs']), int(g['iq_len']), mode=mode) as rx:\n"
+        "            grp = rx.add_group(float(g['period']))\n"
+        "            for f, s in zip(g['freqs'], g['scales']): rx.add_channel(grp, int(f), float(s))\n"
+        "            rx.push_iq(g['iq'])\n"
+        "            out, wi = rx.end_slot_numpy(grp)\n"
+        "        for c in range(len(g['freqs'])):\n"
+        "            d = np.abs(out[c][:wi].astype(np.int32) - g['i16'][c].astype(np.int32)).max()\n"
+        "            assert d <= (0 if mode == cw.MODE_EXACT else 1), (path, mode, c, int(d))\n"
+        "print('carry ok')\n")
+    env = dict(os.environ, CWSL_TILES_PER_SEG=tiles)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "carry ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
 def test_managed_host_buffer_partial_copy(gpu, ref):
     """cwsl_host_alloc buffers: only possibly-non-zero columns cross PCIe; result must equal the full copy,
     including when a later slot is SHORTER than the previous one in the same buffer."""

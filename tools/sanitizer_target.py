@@ -1,0 +1,24 @@
+"""Small target for compute-sanitizer (memcheck / racecheck / synccheck): both kernels, several tiles and
+segments, channel groups, ring wrap, partial last tile."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import cwsl_digi_b200 as cw
+from cwsl_digi_b200 import synth
+
+FS, IQ_LEN = 192000, 2048
+freqs = [int(f) for f in synth.stress_demod_freqs(40)]          # 2 channel groups (32 + 8)
+iq = synth.receiver_iq(70 * IQ_LEN, FS, freqs[:2], receiver=0, tones_per_channel=1)
+for mode in (cw.MODE_FAST, cw.MODE_EXACT):
+    with cw.Receiver(0, FS, IQ_LEN, ring_seconds=0.3, mode=mode) as rx:
+        g = rx.add_group(15.0)
+        for f in freqs:
+            rx.add_channel(g, f, 0.9)
+        for b in range(0, 70, 7):
+            rx.push_iq(iq[b * IQ_LEN * 2:(b + 7) * IQ_LEN * 2])
+        out, wi = rx.end_slot_numpy(g)
+        print("mode", mode, "wi", wi, "checksum", int(out.astype(np.int64).sum()))
+print("done")
