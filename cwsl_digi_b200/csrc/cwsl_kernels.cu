@@ -8,16 +8,19 @@
 //   audio[b] = {+Re, -Im*sign, -Re, +Im*sign}[b & 3] of y_c[b]
 // P_c[k] = phase_inc_c^k by the reference's float recurrence (phase table, built once per channel).
 //
-// Two kernels:
-//   demod_exact_kernel : one thread per output, every float op unfused in the reference's order
-//                        -> bit-identical to oracle/_ref.
-//   demod_fast_kernel  : one thread per R consecutive blocks; the IQ rows are staged into shared
-//                        memory by the TMA bulk-copy engine (cp.async.bulk + mbarrier) once per CTA
-//                        and re-used by all channels the CTA walks; mix and FIR are packed
-//                        fma.rn.f32x2 (FFMA2) with the real tap broadcast from a uniform register
-//                        (constant bank), so the 512-MAC inner product has no load at all; partial
-//                        sums are exchanged through shared memory; Weaver select, max|x| and the
-//                        float audio store are fused in the epilogue.
+// Kernels:
+//   demod_fast_kernel        FAST mode. One thread per R consecutive blocks; the IQ rows of a tile are
+//                            staged into shared memory by the TMA bulk-copy engine (cp.async.bulk +
+//                            mbarrier) and re-used by all channels the CTA walks; mix and FIR are packed
+//                            fma.rn.f32x2 (FFMA2) with the symmetric taps folded and every coefficient an
+//                            FFMA2 immediate, so the inner product issues no load at all; partial sums are
+//                            exchanged through shared memory and carried across tiles; Weaver select,
+//                            max|x| and the float audio store are fused in the epilogue.
+//   demod_exact_tiled_kernel EXACT mode. The reference's loop structure with one thread per block, every
+//                            float operation unfused in the reference's order -> bit-identical.
+//   demod_exact_kernel       EXACT mode, independent one-thread-per-output implementation (cross-check).
+//   quantise_kernel          prepareAudio + int16 conversion for all channels.
+//   phase_table_kernel       the float phase recurrence, one thread per table.
 #include "cwsl_kernels.hpp"
 
 #include <algorithm>
@@ -27,15 +30,13 @@
 namespace cwsl {
 
 // ------------------------------------------------------------------------------------------
-// Constant-bank taps. natural: h[BS*n+m]; transposed: ht[m*32+n] (what the fast kernel walks).
-// One pair per supported block size (Fs = 12000*BS), so receivers of different rates coexist.
+// Constant-bank taps h[BS*n+m] for the gather EXACT kernel, one array per supported block size
+// (Fs = 12000*BS), so receivers of different rates coexist. (The tiled EXACT kernel and the FAST kernel
+// use the same values baked into the instruction stream, see cwsl_taps_baked.inc.)
 // ------------------------------------------------------------------------------------------
 __constant__ float c_h16[512];
-__constant__ float c_ht16[512];
 __constant__ float c_h8[256];
-__constant__ float c_ht8[256];
 __constant__ float c_h4[128];
-__constant__ float c_ht4[128];
 
 template <int BS>
 __device__ __forceinline__ float tap_nat(int i) {
@@ -43,31 +44,13 @@ __device__ __forceinline__ float tap_nat(int i) {
     else if constexpr (BS == 8) return c_h8[i];
     else return c_h4[i];
 }
-template <int BS>
-__device__ __forceinline__ float tap_tr(int i) {
-    if constexpr (BS == 16) return c_ht16[i];
-    else if constexpr (BS == 8) return c_ht8[i];
-    else return c_ht4[i];
-}
-
 cudaError_t upload_taps(uint32_t block_size, const float* taps) {
     const uint32_t n = 32 * block_size;
-    float tr[512];
-    for (uint32_t m = 0; m < block_size; ++m)
-        for (uint32_t k = 0; k < 32; ++k) tr[m * 32 + k] = taps[block_size * k + m];
-    cudaError_t e;
     switch (block_size) {
-        case 16:
-            if ((e = cudaMemcpyToSymbol(c_h16, taps, n * sizeof(float))) != cudaSuccess) return e;
-            return cudaMemcpyToSymbol(c_ht16, tr, n * sizeof(float));
-        case 8:
-            if ((e = cudaMemcpyToSymbol(c_h8, taps, n * sizeof(float))) != cudaSuccess) return e;
-            return cudaMemcpyToSymbol(c_ht8, tr, n * sizeof(float));
-        case 4:
-            if ((e = cudaMemcpyToSymbol(c_h4, taps, n * sizeof(float))) != cudaSuccess) return e;
-            return cudaMemcpyToSymbol(c_ht4, tr, n * sizeof(float));
-        default:
-            return cudaErrorInvalidValue;
+        case 16: return cudaMemcpyToSymbol(c_h16, taps, n * sizeof(float));
+        case 8: return cudaMemcpyToSymbol(c_h8, taps, n * sizeof(float));
+        case 4: return cudaMemcpyToSymbol(c_h4, taps, n * sizeof(float));
+        default: return cudaErrorInvalidValue;
     }
 }
 
@@ -279,10 +262,11 @@ struct FastCfg {
     static constexpr size_t kToneBytes = (size_t)kFastGMax * BS * 8;
     static constexpr size_t kCarryBytes = (size_t)kFastGMax * 31 * 8;
     // 2 CTAs/SM need 2*(kSmem + 1 KB reserved) <= 228 KB: 115 472 B for <16,4,128>
-    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + kCarryBytes + 16;
+    static constexpr size_t kSignBytes = (size_t)kFastGMax * 4;
+    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + kCarryBytes + kSignBytes + 16;
 };
 
-template <int BS, int R, int NT, int CTAS>
+template <int BS, int R, int NT, int CTAS, bool PF>
 __global__ void __launch_bounds__(NT, CTAS)
     demod_fast_kernel(DemodLaunch p, uint32_t ch_per_cta, uint32_t tiles_per_seg) {
     using Cfg = FastCfg<BS, R, NT>;
@@ -294,8 +278,10 @@ __global__ void __launch_bounds__(NT, CTAS)
     float2* O = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kEBytes);
     float4* tone_s = reinterpret_cast<float4*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes);
     float2* carry_s = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes);
+    float* sign_s = reinterpret_cast<float*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes +
+                                             Cfg::kCarryBytes);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes +
-                                                Cfg::kCarryBytes);
+                                                Cfg::kCarryBytes + Cfg::kSignBytes);
 
     const int t = threadIdx.x;
     const uint32_t c0 = blockIdx.y * ch_per_cta;
@@ -313,6 +299,7 @@ __global__ void __launch_bounds__(NT, CTAS)
     }
     for (uint32_t i = t; i < nch * (BS / 2); i += NT)
         tone_s[i] = reinterpret_cast<const float4*>(p.tone)[(size_t)c0 * (BS / 2) + i];
+    for (uint32_t i = t; i < nch; i += NT) sign_s[i] = p.sign[c0 + i];
     __syncthreads();
 
     const float4* __restrict__ xrow = reinterpret_cast<const float4*>(xs + (size_t)t * Cfg::kRowStride);
@@ -352,6 +339,18 @@ __global__ void __launch_bounds__(NT, CTAS)
         }
         mbar_wait(bar_a, tile & 1u);
 
+        // IQ samples and tone entries of the NEXT block to be mixed live in registers: they are dead as soon
+        // as the block is mixed, so the next block's are fetched right then and their LDS latency hides under
+        // the ~340 FFMA2 of the FIR (the rows are the same for every channel, only the tones change)
+        float4 xq[BS / 2], tq[BS / 2];
+        if (PF && row_valid) {
+#pragma unroll
+            for (int m2 = 0; m2 < BS / 2; ++m2) {
+                xq[m2] = xrow[m2];
+                tq[m2] = tone_s[m2];
+            }
+        }
+
         for (uint32_t ci = 0; ci < nch; ++ci) {
             const uint32_t c = c0 + ci;
             // acc[i] = partial sum for output offset (blocks done so far) + i
@@ -368,7 +367,6 @@ __global__ void __launch_bounds__(NT, CTAS)
 #pragma unroll
                     for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
                 }
-                const float4* __restrict__ tn = tone_s + (size_t)ci * (BS / 2);
 #pragma unroll 1
                 for (int r = 0; r < R; ++r) {
                     float4 Pq = Pcur[0];
@@ -379,8 +377,8 @@ __global__ void __launch_bounds__(NT, CTAS)
                     float2 v[BS];
 #pragma unroll
                     for (int m2 = 0; m2 < BS / 2; ++m2) {
-                        const float4 xx = xrow[r * (BS / 2) + m2];  // two IQ samples
-                        const float4 tt = tn[m2];                  // their two tone entries
+                        const float4 xx = PF ? xq[m2] : xrow[r * (BS / 2) + m2];                    // two IQ samples
+                        const float4 tt = PF ? tq[m2] : tone_s[(size_t)ci * (BS / 2) + m2];        // their two tone entries
 #pragma unroll
                         for (int s = 0; s < 2; ++s) {
                             const float2 tn_m = s ? make_float2(tt.z, tt.w) : make_float2(tt.x, tt.y);
@@ -389,6 +387,18 @@ __global__ void __launch_bounds__(NT, CTAS)
                             const float xr = s ? xx.z : xx.x, xi = s ? xx.w : xx.y;
                             float2 vv = fmul2(w, bc(xr));
                             v[2 * m2 + s] = ffma2(make_float2(-w.y, w.x), bc(xi), vv);
+                        }
+                    }
+                    // fetch the next block's samples/tones (next r, or block 0 of the next channel)
+                    if constexpr (PF) {
+                        const int rn = (r + 1 == R) ? 0 : r + 1;
+                        const uint32_t cn = (r + 1 == R) ? min(ci + 1, nch - 1) : ci;
+                        const float4* __restrict__ xn = xrow + rn * (BS / 2);
+                        const float4* __restrict__ tn = tone_s + (size_t)cn * (BS / 2);
+#pragma unroll
+                        for (int m2 = 0; m2 < BS / 2; ++m2) {
+                            xq[m2] = xn[m2];
+                            tq[m2] = tn[m2];
                         }
                     }
                     // FIR: tap row n of this block feeds output offset 31-n
@@ -447,7 +457,7 @@ __global__ void __launch_bounds__(NT, CTAS)
             // ---- epilogue: Weaver select, float audio store, max|x| ----
             float lmax = 0.0f;
             if (writes) {
-                const float sign = p.sign[c];
+                const float sign = sign_s[ci];
                 float o4[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
@@ -690,12 +700,12 @@ cudaError_t launch_demod_exact_gather(const DemodLaunch& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <int BS, int R, int NT, int CTAS>
+template <int BS, int R, int NT, int CTAS, bool PF>
 static cudaError_t launch_fast_t(const DemodLaunch& p, cudaStream_t s) {
     using Cfg = FastCfg<BS, R, NT>;
     static bool attr_done = false;
     static int sms = 0;
-    auto kern = demod_fast_kernel<BS, R, NT, CTAS>;
+    auto kern = demod_fast_kernel<BS, R, NT, CTAS, PF>;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
         if (e != cudaSuccess) return e;
@@ -727,10 +737,17 @@ cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
 
 cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s) {
     if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
+    // CWSL_FAST_PREFETCH=1: keep the next block's samples/tones in registers (fetched right after the mix).
+    // Measured SLOWER on B200 (563.7 vs 573.4 G ch-samples/s: the 64 extra live registers cost more than the
+    // shared-memory latency they hide); kept as a documented negative result.
+    static const bool pf = [] {
+        const char* e = std::getenv("CWSL_FAST_PREFETCH");
+        return e && e[0] == '1';
+    }();
     switch (p.block_size) {
-        case 16: return launch_fast_t<16, 4, 128, 2>(p, s);
-        case 8: return launch_fast_t<8, 4, 128, 2>(p, s);
-        case 4: return launch_fast_t<4, 4, 128, 2>(p, s);
+        case 16: return pf ? launch_fast_t<16, 4, 128, 2, true>(p, s) : launch_fast_t<16, 4, 128, 2, false>(p, s);
+        case 8: return launch_fast_t<8, 4, 128, 2, false>(p, s);
+        case 4: return launch_fast_t<4, 4, 128, 2, false>(p, s);
         default: return cudaErrorInvalidValue;
     }
 }
