@@ -11,3 +11,4 @@
 #include "Config.hpp"
 #include "SlotClock.hpp"
 #include "CwslSharedMemory.hpp"
+#include "Jt9SharedMemory.hpp"

@@ -199,6 +199,29 @@ int main(int argc, char** argv) {
         EXPECT(!missing.open("CWSL_no_such_band"));
     }
 
+    // ---- jt9 shared-memory block (source/DecoderPool.hpp:44-108, :421-593) ----
+    {
+        std::unique_ptr<dec_data_t> dd(new dec_data_t);
+        std::vector<std::int16_t> audio(240000);
+        for (size_t i = 0; i < audio.size(); ++i) audio[i] = static_cast<std::int16_t>(i % 1000 - 500);
+        ItemToDecode ft8(audio, "FT8", 1792214520, 14074000, 3, "cwd", 15.0f);
+        EXPECT(fillDecData(dd.get(), ft8, 6000, 3));
+        EXPECT(dd->params.nmode == 8 && dd->params.ntrperiod == 15 && dd->params.lft8apon && dd->params.napwid == 50);
+        EXPECT(dd->params.nfa == 0 && dd->params.nfb == 6000 && dd->params.ndepth == 3 && dd->params.newdat && dd->params.dttol == 4.0f);
+        EXPECT(dd->ipc[0] == 0 && dd->ipc[1] == 1 && dd->ipc[2] == -1);
+        EXPECT(dd->d2[0] == audio[0] && dd->d2[239999] == audio[239999] && dd->d2[240000] == 0);
+        ItemToDecode ft4(std::vector<std::int16_t>(150000, 7), "FT4", 0, 14080000, 4, "cwd", 7.5f);
+        EXPECT(fillDecData(dd.get(), ft4, 3000, 2) && dd->params.nmode == 5 && dd->params.ntrperiod == 7 && dd->params.napwid == 80);
+        EXPECT(dd->d2[149999] == 7 && dd->d2[150000] == 0);   // block is cleared first
+        ItemToDecode f4w(std::vector<std::int16_t>(21660000, 1), "FST4W-1800", 0, 474200, 5, "cwd", 1800.0f);
+        EXPECT(fillDecData(dd.get(), f4w, 3000, 3) && dd->params.nmode == 241 && dd->params.nzhsym == 6232 && dd->ipc[0] == 6232);
+        EXPECT(dd->params.nfqso == 1500 && dd->params.nexp_decode == 768 && dd->d2[NTMAX * RX_SAMPLE_RATE - 1] == 1);  // clipped at NTMAX
+        ItemToDecode f300(audio, "FST4-300", 0, 474200, 6, "cwd", 300.0f);
+        EXPECT(fillDecData(dd.get(), f300, 3000, 3) && dd->params.nfa == 700 && dd->params.nfb == 1100 && dd->params.ndepth == 1 && dd->params.nmode == 240);
+        ItemToDecode wspr(audio, "WSPR", 0, 14095600, 7, "cwd", 120.0f);
+        EXPECT(!fillDecData(dd.get(), wspr, 3000, 3));           // WSPR always goes through a WAV file
+    }
+
     if (g_fail) {
         std::fprintf(stderr, "%d host test(s) failed\n", g_fail);
         return 1;
