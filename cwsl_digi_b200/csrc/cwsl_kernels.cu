@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 namespace cwsl {
 
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(NT, CTAS)
 
     for (uint32_t tile = 0; tile < tiles_per_seg; ++tile) {
         const int64_t kt0 = seg_b0 - 32 + (int64_t)tile * Cfg::kTile;
-        if (kt0 + 32 >= seg_b1 && tile > 0) break;  // nothing left to output
+        if (tile > 0 && kt0 >= seg_b1) break;  // nothing left to output (tiles after the first start AT kt0)
         const int64_t kbase = kt0 + (int64_t)t * R;
         const bool row_valid = kbase >= 0 && kbase + R <= (int64_t)p.b1;
         // threads whose outputs are written: inside the segment; the overlap rows of the first tile are not
@@ -517,17 +518,15 @@ static uint32_t choose_tiles_per_seg(uint32_t n_out, uint32_t tile, uint32_t ch_
 // a tile owe to the next tile's first 31 outputs are carried in shared memory (a prefix of the same
 // ordered sum, hence still bit-identical).
 // ------------------------------------------------------------------------------------------
-constexpr int kExactGMax = 24;  // channels per CTA: keeps 2 CTAs (16 warps) per SM within 228 KB of shared memory
-
-template <int BS, int NT>
+template <int BS, int NT, int G>  // G = channels walked per CTA
 struct ExactCfg {
     static constexpr int kRowBytes = BS * 8;
     static constexpr int kRowStride = kRowBytes + 16;   // conflict-free per-thread LDS.128
     static constexpr int kDStride = 33;                 // float2 per D row (32 + 1 pad: conflict-free both ways)
     static constexpr size_t kXBytes = (size_t)NT * kRowStride;
     static constexpr size_t kDBytes = (size_t)NT * kDStride * 8;
-    static constexpr size_t kToneBytes = (size_t)kExactGMax * BS * 8;
-    static constexpr size_t kCarryBytes = (size_t)kExactGMax * 31 * 8;
+    static constexpr size_t kToneBytes = (size_t)G * BS * 8;
+    static constexpr size_t kCarryBytes = (size_t)G * 31 * 8;
     static constexpr size_t kSmem = kXBytes + kDBytes + kToneBytes + kCarryBytes + 16;
 };
 
@@ -539,10 +538,10 @@ __device__ __forceinline__ float2 cmul_unfused(float2 x, float2 y) {
     return make_float2(__fsub_rn(p.x, q.x), __fadd_rn(p.y, q.y));  // (ac - bd, ad + bc), scalar: see add_unfused
 }
 
-template <int BS, int NT>
-__global__ void __launch_bounds__(NT, 2)
+template <int BS, int NT, int CTAS, int G>
+__global__ void __launch_bounds__(NT, CTAS)
     demod_exact_tiled_kernel(DemodLaunch p, uint32_t ch_per_cta, uint32_t tiles_per_seg) {
-    using Cfg = ExactCfg<BS, NT>;
+    using Cfg = ExactCfg<BS, NT, G>;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* xs = smem;
     float2* D = reinterpret_cast<float2*>(smem + Cfg::kXBytes);
@@ -572,7 +571,7 @@ __global__ void __launch_bounds__(NT, 2)
 
     for (uint32_t tile = 0; tile < tiles_per_seg; ++tile) {
         const int64_t kt0 = seg_b0 - 31 + (int64_t)tile * NT;
-        if (kt0 + 31 >= seg_b1 && tile > 0) break;
+        if (tile > 0 && kt0 >= seg_b1) break;  // tiles after the first output from kt0 on
         const int64_t k = kt0 + t;  // my block = my output
         const bool row_valid = k >= 0 && k < (int64_t)p.b1;
         const bool writes = row_valid && k >= seg_b0 && k < seg_b1;
@@ -661,12 +660,12 @@ __global__ void __launch_bounds__(NT, 2)
     }
 }
 
-template <int BS, int NT>
+template <int BS, int NT, int CTAS, int G>
 static cudaError_t launch_exact_t(const DemodLaunch& p, cudaStream_t s) {
-    using Cfg = ExactCfg<BS, NT>;
+    using Cfg = ExactCfg<BS, NT, G>;
     static bool attr_done = false;
     static int sms = 0;
-    auto kern = demod_exact_tiled_kernel<BS, NT>;
+    auto kern = demod_exact_tiled_kernel<BS, NT, CTAS, G>;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
         if (e != cudaSuccess) return e;
@@ -677,9 +676,9 @@ static cudaError_t launch_exact_t(const DemodLaunch& p, cudaStream_t s) {
         attr_done = true;
     }
     const uint32_t n_out = p.b1 - p.b0;
-    const uint32_t g = p.n_channels < (uint32_t)kExactGMax ? p.n_channels : (uint32_t)kExactGMax;
+    const uint32_t g = p.n_channels < (uint32_t)G ? p.n_channels : (uint32_t)G;
     const uint32_t groups = (p.n_channels + g - 1) / g;
-    const uint32_t l = choose_tiles_per_seg(n_out, NT, groups, (uint32_t)sms * 2, 31);
+    const uint32_t l = choose_tiles_per_seg(n_out, NT, groups, (uint32_t)sms * CTAS, 31);
     const uint32_t seg_out = l * NT - 31;
     dim3 grid((n_out + seg_out - 1) / seg_out, groups);
     kern<<<grid, NT, Cfg::kSmem, s>>>(p, g, l);
@@ -727,10 +726,16 @@ static cudaError_t launch_fast_t(const DemodLaunch& p, cudaStream_t s) {
 
 cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
     if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
+    // CWSL_EXACT_SHAPE=256x2 selects 256-thread CTAs, 2 per SM (16 warps/SM); default 128x3 (12 warps/SM, cheaper
+    // barriers: measured below)
+    static const bool big = [] {
+        const char* e = std::getenv("CWSL_EXACT_SHAPE");
+        return e && std::string(e) == "256x2";
+    }();
     switch (p.block_size) {
-        case 16: return launch_exact_t<16, 256>(p, s);
-        case 8: return launch_exact_t<8, 256>(p, s);
-        case 4: return launch_exact_t<4, 256>(p, s);
+        case 16: return big ? launch_exact_t<16, 256, 2, 24>(p, s) : launch_exact_t<16, 128, 3, 32>(p, s);
+        case 8: return launch_exact_t<8, 128, 3, 32>(p, s);
+        case 4: return launch_exact_t<4, 128, 3, 32>(p, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -374,7 +374,7 @@ def test_stress_exact_spot_channels(stress_run, ref):
         assert np.array_equal(out[i], o["i16"])
 
 
-@pytest.mark.parametrize("tiles", ["2", "5"])
+@pytest.mark.parametrize("tiles", ["2", "3", "5", "7"])
 def test_forced_cross_tile_carry(gpu, tiles):
     """Both kernels with the segment length pinned (CWSL_TILES_PER_SEG) so that the cross-tile carry path runs
     on a small input; checked against the committed golden vectors in a subprocess (the knob is read once)."""
@@ -394,6 +394,18 @@ def test_forced_cross_tile_carry(gpu, tiles):
         "        for c in range(len(g['freqs'])):\n"
         "            d = np.abs(out[c][:wi].astype(np.int32) - g['i16'][c].astype(np.int32)).max()\n"
         "            assert d <= (0 if mode == cw.MODE_EXACT else 1), (path, mode, c, int(d))\n"
+        "# remainders of every size in the last tile of the last segment: compare FAST vs EXACT-gather-free truth\n"
+        "from oracle.oracle import Port\n"
+        "port = Port(); g = np.load('tests/golden/ft8_192k.npz'); fs = int(g['fs'])\n"
+        "for nblk in range(1, 25):\n"
+        "    iq = g['iq'][:nblk * 2048 * 2]\n"
+        "    o = port.slot(fs, int(g['freqs'][0]), iq, 2048, 0.9, int(g['af_size']))\n"
+        "    for mode in (cw.MODE_EXACT, cw.MODE_FAST):\n"
+        "        with cw.Receiver(0, fs, 2048, mode=mode) as rx:\n"
+        "            grp = rx.add_group(15.0); rx.add_channel(grp, int(g['freqs'][0]), 0.9)\n"
+        "            rx.push_iq(iq); out, wi = rx.end_slot_numpy(grp)\n"
+        "        d = np.abs(out[0].astype(np.int32) - o['i16'].astype(np.int32)).max()\n"
+        "        assert wi == o['write_index'] and d <= (0 if mode == cw.MODE_EXACT else 1), (nblk, mode, int(d))\n"
         "print('carry ok')\n")
     env = dict(os.environ, CWSL_TILES_PER_SEG=tiles)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
