@@ -406,6 +406,16 @@ def test_forced_cross_tile_carry(gpu, tiles):
         "            rx.push_iq(iq); out, wi = rx.end_slot_numpy(grp)\n"
         "        d = np.abs(out[0].astype(np.int32) - o['i16'].astype(np.int32)).max()\n"
         "        assert wi == o['write_index'] and d <= (0 if mode == cw.MODE_EXACT else 1), (nblk, mode, int(d))\n"
+        "# streaming through a small ring (wrap) with the carry path forced\n"
+        "iq = g['iq']; o = port.slot(fs, int(g['freqs'][1]), iq, 2048, 0.9, int(g['af_size']))\n"
+        "for mode in (cw.MODE_EXACT, cw.MODE_FAST):\n"
+        "    with cw.Receiver(0, fs, 2048, ring_seconds=0.12, mode=mode) as rx:\n"
+        "        grp = rx.add_group(15.0); rx.add_channel(grp, int(g['freqs'][1]), 0.9)\n"
+        "        for b in range(0, 24, 5):\n"
+        "            rx.push_iq(iq[b * 4096:(b + 5) * 4096]); rx.process(grp)\n"
+        "        out, wi = rx.end_slot_numpy(grp)\n"
+        "    d = np.abs(out[0].astype(np.int32) - o['i16'].astype(np.int32)).max()\n"
+        "    assert wi == o['write_index'] and d <= (0 if mode == cw.MODE_EXACT else 1), ('stream', mode, int(d))\n"
         "print('carry ok')\n")
     env = dict(os.environ, CWSL_TILES_PER_SEG=tiles)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
