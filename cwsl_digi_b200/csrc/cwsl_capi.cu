@@ -187,6 +187,15 @@ void free_group_device(Group& g) {
 int commit(cwsl_rx* rx) {
     if (rx->committed) return CWSL_OK;
     if (rx->groups.empty()) return fail(CWSL_ERR_STATE, "no slot group defined");
+    // One-time setup of this receiver allocates GBs of device memory. Do it on a quiet device: with more than
+    // ~8 receivers on private non-blocking streams, cudaMalloc overlapping other receivers' running kernels
+    // ended in "illegal memory access" on driver 580 / CUDA 12.9 (any kernel, TMA or not; compute-sanitizer
+    // clean). CWSL_COMMIT_NOSYNC=1 disables the synchronisation (diagnostics only).
+    static const bool nosync = [] {
+        const char* e = std::getenv("CWSL_COMMIT_NOSYNC");
+        return e && e[0] == '1';
+    }();
+    if (!nosync) CK(cudaDeviceSynchronize());
     // constant-bank taps (once per device and block size), cross-checked against the baked copy
     {
         std::lock_guard<std::mutex> lk(g_mu);
