@@ -302,6 +302,7 @@ int ensure_ring(cwsl_rx* rx) {
         blocks = std::max<uint64_t>(blocks, 4 * (uint64_t)rx->sub + 64);
         blocks = (blocks + quantum - 1) / quantum * quantum;
         rx->own_ring_blocks = (uint32_t)blocks;
+        CK(cudaDeviceSynchronize());  // allocate on a quiet device, see commit()
         CK(cudaMalloc(&rx->d_ring, (size_t)blocks * rx->geo.block_size * sizeof(float2)));
     }
     if (rx->bound || rx->ring_ptr != rx->d_ring) {
