@@ -248,10 +248,12 @@ int commit(cwsl_rx* rx) {
         // phase tables: one per distinct (Fs, demodFreq, sideband, length), shared process-wide
         const uint32_t length = (uint32_t)((g.af_size + 3) / 4 * 4 + 4);
         std::vector<const float2*> ptrs(C);
-        std::vector<float2> new_inc;
-        std::vector<float2*> new_tab;
         {
+            // The cache lock is held until the new tables are BUILT: another thread setting up a receiver with
+            // the same frequencies must never see a table that is allocated but not yet filled.
             std::lock_guard<std::mutex> lk(g_mu);
+            std::vector<float2> new_inc;
+            std::vector<float2*> new_tab;
             for (uint32_t c = 0; c < C; ++c) {
                 PhaseKey k{rx->device, rx->fs, g.ch[c].demod_freq, g.ch[c].usb, length};
                 PhaseEntry& e = g_phase_cache[k];
@@ -268,20 +270,20 @@ int commit(cwsl_rx* rx) {
                 g.phase_keys.push_back(k);
                 ptrs[c] = e.table;
             }
+            if (!new_tab.empty()) {
+                float2* d_inc = nullptr;
+                float2** d_tab = nullptr;
+                CK(cudaMalloc(&d_inc, new_inc.size() * sizeof(float2)));
+                CK(cudaMalloc((void**)&d_tab, new_tab.size() * sizeof(float2*)));
+                CK(cudaMemcpy(d_inc, new_inc.data(), new_inc.size() * sizeof(float2), cudaMemcpyHostToDevice));
+                CK(cudaMemcpy((void*)d_tab, new_tab.data(), new_tab.size() * sizeof(float2*), cudaMemcpyHostToDevice));
+                CK(cwsl::launch_phase_tables(d_inc, d_tab, (uint32_t)new_tab.size(), length, rx->stream));
+                CK(cudaStreamSynchronize(rx->stream));
+                cudaFree(d_inc);
+                cudaFree((void*)d_tab);
+            }
         }
         CK(cudaMemcpy((void*)g.d_phase, ptrs.data(), C * sizeof(float2*), cudaMemcpyHostToDevice));
-        if (!new_tab.empty()) {
-            float2* d_inc = nullptr;
-            float2** d_tab = nullptr;
-            CK(cudaMalloc(&d_inc, new_inc.size() * sizeof(float2)));
-            CK(cudaMalloc((void**)&d_tab, new_tab.size() * sizeof(float2*)));
-            CK(cudaMemcpy(d_inc, new_inc.data(), new_inc.size() * sizeof(float2), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy((void*)d_tab, new_tab.data(), new_tab.size() * sizeof(float2*), cudaMemcpyHostToDevice));
-            CK(cwsl::launch_phase_tables(d_inc, d_tab, (uint32_t)new_tab.size(), length, rx->stream));
-            CK(cudaStreamSynchronize(rx->stream));
-            cudaFree(d_inc);
-            cudaFree((void*)d_tab);
-        }
     }
     rx->max_slot_blocks = max_blocks;
     rx->committed = true;

@@ -26,7 +26,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <set>
 #include <string>
+#include <utility>
 
 namespace cwsl {
 
@@ -477,6 +480,34 @@ __global__ void __launch_bounds__(NT, CTAS)
     }
 }
 
+// Opt the kernel in to its dynamic shared memory size (per device: function attributes are per context) and
+// return the SM count of the current device. Cheap enough to call on every launch; thread-safe.
+static cudaError_t prepare_kernel(const void* kern, int smem_bytes, int* sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    static int sm_count[64] = {0};
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done.count({kern, dev})) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return e;
+        done.insert({kern, dev});
+    }
+    if (dev >= 0 && dev < 64) {
+        if (sm_count[dev] == 0) {
+            int n = 0;
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            sm_count[dev] = n > 0 ? n : 148;
+        }
+        *sms = sm_count[dev];
+    } else {
+        *sms = 148;
+    }
+    return cudaSuccess;
+}
+
 // Tiles per segment: trade the 32-block overlap paid once per segment against the tail of the last
 // wave of CTAs. Cost model in block units, minimised over L.
 static uint32_t choose_tiles_per_seg(uint32_t n_out, uint32_t tile, uint32_t ch_groups, uint32_t slots,
@@ -663,18 +694,9 @@ __global__ void __launch_bounds__(NT, CTAS)
 template <int BS, int NT, int CTAS, int G>
 static cudaError_t launch_exact_t(const DemodLaunch& p, cudaStream_t s) {
     using Cfg = ExactCfg<BS, NT, G>;
-    static bool attr_done = false;
-    static int sms = 0;
     auto kern = demod_exact_tiled_kernel<BS, NT, CTAS, G>;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
-        if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-        attr_done = true;
-    }
+    int sms = 0;
+    if (cudaError_t e = prepare_kernel((const void*)kern, (int)Cfg::kSmem, &sms); e != cudaSuccess) return e;
     const uint32_t n_out = p.b1 - p.b0;
     const uint32_t g = p.n_channels < (uint32_t)G ? p.n_channels : (uint32_t)G;
     const uint32_t groups = (p.n_channels + g - 1) / g;
@@ -702,18 +724,9 @@ cudaError_t launch_demod_exact_gather(const DemodLaunch& p, cudaStream_t s) {
 template <int BS, int R, int NT, int CTAS, bool PF>
 static cudaError_t launch_fast_t(const DemodLaunch& p, cudaStream_t s) {
     using Cfg = FastCfg<BS, R, NT>;
-    static bool attr_done = false;
-    static int sms = 0;
     auto kern = demod_fast_kernel<BS, R, NT, CTAS, PF>;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
-        if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-        attr_done = true;
-    }
+    int sms = 0;
+    if (cudaError_t e = prepare_kernel((const void*)kern, (int)Cfg::kSmem, &sms); e != cudaSuccess) return e;
     const uint32_t n_out = p.b1 - p.b0;
     const uint32_t g = p.n_channels < (uint32_t)kFastGMax ? p.n_channels : (uint32_t)kFastGMax;
     const uint32_t groups = (p.n_channels + g - 1) / g;

@@ -446,6 +446,41 @@ def test_managed_host_buffer_partial_copy(gpu, ref):
     buf.free()
 
 
+def test_concurrent_receivers_from_threads(gpu):
+    """Different handles driven from different host threads (ctypes drops the GIL): every thread must get the
+    golden result; 12 receivers > the 8 default hardware queues, set up while others are already running."""
+    import threading
+    cw = gpu
+    with np.load(GOLDEN[1]) as z:   # ft8_192k; materialise first: NpzFile is not thread-safe
+        g = {k: z[k] for k in z.files}
+    fs, iq_len = int(g["fs"]), int(g["iq_len"])
+    errors = []
+
+    def worker(i):
+        try:
+            mode = cw.MODE_EXACT if i % 2 else cw.MODE_FAST
+            for rep in range(3):
+                with cw.Receiver(0, fs, iq_len, mode=mode) as rx:
+                    grp = rx.add_group(float(g["period"]))
+                    for f, s_ in zip(g["freqs"], g["scales"]):
+                        rx.add_channel(grp, int(f), float(s_))
+                    rx.push_iq(g["iq"])
+                    out, wi = rx.end_slot_numpy(grp)
+                for c in range(len(g["freqs"])):
+                    d = np.abs(out[c][:wi].astype(np.int32) - g["i16"][c].astype(np.int32)).max()
+                    if wi != int(g["write_index"][c]) or d > (0 if mode == cw.MODE_EXACT else 1):
+                        errors.append((i, rep, c, int(d)))
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(12)]
+    for t_ in threads:
+        t_.start()
+    for t_ in threads:
+        t_.join()
+    assert not errors, errors[:5]
+
+
 # ---- error behaviour mirrors the reference's exceptions / config checks --------------------------
 def test_error_behaviour(gpu):
     cw = gpu
