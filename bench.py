@@ -316,27 +316,31 @@ def run_b200(a):
     if not a.no_e2e:
         for rx in rxs:
             rx.synchronize()
-        NBUF = min(4, len(rxs))
+        NBUF = min(int(os.environ.get("CWSL_BENCH_E2E_BUFFERS", "4")), len(rxs))
         host_in = [torch.empty(2 * n_iq, dtype=torch.float32).pin_memory() for _ in my_rx]
         for h, x in zip(host_in, iq_dev):
             h.copy_(x)
         # hand-off buffers from cwsl_host_alloc: pinned, and the library skips the known-zero tail on the wire
         host_out = [cw.HostBuffer(a.channels, afs) for _ in range(NBUF)]
-        streams = [torch.cuda.Stream() for _ in range(NBUF)]
-        for i in range(len(my_rx)):
-            rxs[i].set_stream(streams[i % NBUF].cuda_stream)
+        # Kernels of all receivers are queued FIFO on ONE compute stream (so receivers finish one after the other,
+        # not all together), the H2D of the next receiver's IQ rides the same stream, and every finished slot is
+        # copied back on its receiver's private copy stream (inside cwsl_rx_end_slot), overlapping the next kernels.
+        e2e_stream = torch.cuda.Stream()
+        for rx in rxs:
+            rx.set_stream(e2e_stream.cuda_stream)
         checks = [0]
 
         def step_e2e():
             for i, rx in enumerate(rxs):
                 b = i % NBUF
                 if i >= NBUF:
-                    streams[b].synchronize()            # previous user of this pinned buffer has landed
+                    rxs[i - NBUF].wait_output()         # previous user of this pinned buffer has landed
                     checks[0] ^= int(host_out[b].array[0, 1000])   # consumer touches the result
                 rx.push_iq((host_in[i].data_ptr(), n_blocks))
                 rx.end_slot(0, host_out[b].ptr)
-            for s in streams:
-                s.synchronize()
+            for rx in rxs[-NBUF:]:
+                rx.wait_output()
+            e2e_stream.synchronize()
 
         for _ in range(2):
             step_e2e()
@@ -359,7 +363,8 @@ def run_b200(a):
                             "the zero tail of the managed (cwsl_host_alloc) buffer is already zero on the host",
                    ms_per_step=1e3 * wall / a.steps,
                    note="pinned host IQ -> cwsl_rx_push_iq -> cwsl_rx_end_slot(host int16); timed region includes "
-                        "every H2D and D2H copy; wall clock around a device synchronize, max over ranks")
+                        "every H2D and D2H copy; wall clock around a device synchronize, max over ranks; "
+                        f"{NBUF} pinned hand-off buffers in rotation")
 
     # ---- BASELINE.json configs[2]: the 8-receiver x 7-mode skimmer station, streamed ----------------------
     station = None

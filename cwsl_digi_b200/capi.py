@@ -17,7 +17,7 @@ SYMBOLS = [
     "cwsl_rx_add_group", "cwsl_rx_add_channel", "cwsl_rx_num_groups", "cwsl_rx_num_channels",
     "cwsl_rx_group_af_size", "cwsl_rx_push_iq", "cwsl_rx_push_iq_device", "cwsl_rx_bind_device_iq",
     "cwsl_rx_process", "cwsl_rx_end_slot", "cwsl_rx_device_audio", "cwsl_rx_copy_device_audio", "cwsl_rx_read_float_audio",
-    "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_stream", "cwsl_rx_set_stream", "cwsl_rx_enable_timing",
+    "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_wait_output", "cwsl_rx_stream", "cwsl_rx_set_stream", "cwsl_rx_enable_timing",
     "cwsl_rx_kernel_times", "cwsl_measure_fp32_peak", "cwsl_host_alloc", "cwsl_host_free",
 ]
 
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.cwsl_rx_read_float_audio.argtypes = [vp, C.c_int, C.c_int, vp]
     L.cwsl_rx_channel_stats.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.cwsl_rx_synchronize.argtypes = [vp]
+    L.cwsl_rx_wait_output.argtypes = [vp]
     L.cwsl_rx_stream.restype = vp
     L.cwsl_rx_stream.argtypes = [vp]
     L.cwsl_rx_set_stream.argtypes = [vp, vp]
@@ -259,6 +260,9 @@ class Receiver:
 
     def synchronize(self) -> None:
         _check(self._L.cwsl_rx_synchronize(self._h))
+
+    def wait_output(self) -> None:
+        _check(self._L.cwsl_rx_wait_output(self._h))
 
     def set_stream(self, cuda_stream: int) -> None:
         _check(self._L.cwsl_rx_set_stream(self._h, cuda_stream))

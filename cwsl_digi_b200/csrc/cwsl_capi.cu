@@ -115,8 +115,12 @@ struct cwsl_rx {
     uint32_t sub = 0;  // SSBD blocks per IQ block
     int mode = CWSL_MODE_FAST;
     double ring_seconds = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // kernels, H2D into the ring
     bool own_stream = true;
+    cudaStream_t copy_stream = nullptr;  // D2H of finished slots, so they overlap the next kernels on `stream`
+    cudaEvent_t ev_out_ready = nullptr;  // recorded on `stream` after quantise of the last slot
+    cudaEvent_t ev_d2h_done = nullptr;   // recorded on `copy_stream` after the last slot's D2H
+    bool d2h_pending = false;
     float2* d_ring = nullptr;        // owned ring (nullptr while bound to external IQ)
     const float2* ring_ptr = nullptr;  // what the kernels read
     uint32_t ring_blocks = 0;
@@ -520,7 +524,10 @@ cwsl_rx_t* cwsl_rx_create(int device, uint32_t sample_rate, uint32_t iq_len, dou
     rx->geo = geo;
     rx->sub = iq_len / geo.block_size;
     rx->ring_seconds = ring_seconds;
-    if (cudaStreamCreateWithFlags(&rx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&rx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&rx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&rx->ev_out_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&rx->ev_d2h_done, cudaEventDisableTiming) != cudaSuccess) {
         fail(CWSL_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
@@ -531,6 +538,7 @@ void cwsl_rx_destroy(cwsl_rx_t* rx) {
     if (!rx) return;
     DeviceGuard dg(rx->device);
     if (rx->stream) cudaStreamSynchronize(rx->stream);
+    if (rx->copy_stream) cudaStreamSynchronize(rx->copy_stream);
     for (Group& g : rx->groups) free_group_device(g);
     cudaFree(rx->d_ring);
     for (auto& pr : rx->ev_demod) {
@@ -543,6 +551,9 @@ void cwsl_rx_destroy(cwsl_rx_t* rx) {
     }
     for (auto e : rx->ev_pool) cudaEventDestroy(e);
     if (rx->stream && rx->own_stream) cudaStreamDestroy(rx->stream);
+    if (rx->copy_stream) cudaStreamDestroy(rx->copy_stream);
+    if (rx->ev_out_ready) cudaEventDestroy(rx->ev_out_ready);
+    if (rx->ev_d2h_done) cudaEventDestroy(rx->ev_d2h_done);
     delete rx;
 }
 
@@ -556,6 +567,8 @@ int cwsl_rx_set_stream(cwsl_rx_t* rx, void* cuda_stream) {
     if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
     DeviceGuard dg(rx->device);
     CK(cudaStreamSynchronize(rx->stream));
+    CK(cudaStreamSynchronize(rx->copy_stream));
+    rx->d2h_pending = false;
     if (rx->own_stream && rx->stream) cudaStreamDestroy(rx->stream);
     rx->stream = static_cast<cudaStream_t>(cuda_stream);
     rx->own_stream = false;
@@ -679,6 +692,8 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
         e1 = get_event(rx);
         CK(cudaEventRecord(e0, rx->stream));
     }
+    // the previous slot's device->host copy (on the copy stream) may still be reading an int16 buffer
+    if (rx->d2h_pending) CK(cudaStreamWaitEvent(rx->stream, rx->ev_d2h_done, 0));
     CK(cwsl::launch_quantise(q, rx->stream));
     CK(cwsl::launch_clear_u32(g->d_maxbits, C, rx->stream));  // next slot starts from max|x| = 0
     if (rx->timing) {
@@ -711,13 +726,19 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
                 }
             }
         }
+        // The copy runs on the receiver's private copy stream, behind an event: the kernels of whatever is queued
+        // next on `stream` (this receiver's next slot, or other receivers sharing the stream) overlap it.
+        CK(cudaEventRecord(rx->ev_out_ready, rx->stream));
+        CK(cudaStreamWaitEvent(rx->copy_stream, rx->ev_out_ready, 0));
         if (cols >= g->af_size) {
             CK(cudaMemcpyAsync(out_i16, g->d_out, (size_t)C * g->af_size * sizeof(int16_t), cudaMemcpyDeviceToHost,
-                               rx->stream));
+                               rx->copy_stream));
         } else if (cols > 0) {
             CK(cudaMemcpy2DAsync(out_i16, g->af_size * sizeof(int16_t), g->d_out, g->af_size * sizeof(int16_t),
-                                 cols * sizeof(int16_t), C, cudaMemcpyDeviceToHost, rx->stream));
+                                 cols * sizeof(int16_t), C, cudaMemcpyDeviceToHost, rx->copy_stream));
         }
+        CK(cudaEventRecord(rx->ev_d2h_done, rx->copy_stream));
+        rx->d2h_pending = true;
     }
     if (write_index) *write_index = (size_t)g->processed;
     g->last_write_index = (size_t)g->processed;
@@ -774,6 +795,18 @@ int cwsl_rx_synchronize(cwsl_rx_t* rx) {
     if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
     DeviceGuard dg(rx->device);
     CK(cudaStreamSynchronize(rx->stream));
+    CK(cudaStreamSynchronize(rx->copy_stream));
+    rx->d2h_pending = false;
+    return CWSL_OK;
+}
+
+int cwsl_rx_wait_output(cwsl_rx_t* rx) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    DeviceGuard dg(rx->device);
+    if (rx->d2h_pending) {
+        CK(cudaEventSynchronize(rx->ev_d2h_done));
+        rx->d2h_pending = false;
+    }
     return CWSL_OK;
 }
 

@@ -159,8 +159,14 @@ int cwsl_rx_read_float_audio(cwsl_rx_t* rx, int group, int channel, float* out);
  * (the values the reference logs, source/Instance.cpp:314,336); synchronous. */
 int cwsl_rx_channel_stats(cwsl_rx_t* rx, int group, int channel, float* max_val, float* factor);
 
-/* Block until all asynchronous work queued on this receiver has finished. */
+/* Block until all asynchronous work queued on this receiver has finished (kernels and copies). */
 int cwsl_rx_synchronize(cwsl_rx_t* rx);
+
+/* Block only until the host copy of the LAST cwsl_rx_end_slot(rx, ..., out_i16, ...) has landed. The copy runs
+ * on a private copy stream behind the slot's kernels, so it overlaps whatever is queued next on the receiver's
+ * stream; use this (not cwsl_rx_synchronize) when several receivers share one stream and only this receiver's
+ * hand-off buffer is needed. */
+int cwsl_rx_wait_output(cwsl_rx_t* rx);
 
 /* The CUDA stream (cudaStream_t) all work of this receiver is queued on, for event timing. */
 void* cwsl_rx_stream(cwsl_rx_t* rx);
