@@ -104,9 +104,18 @@ inline void Receiver::finishSlot(SlotGroup& g) {
     // source/Instance.cpp:203-253 for every decoder of the group
     const std::uint64_t now = std::chrono::system_clock::now().time_since_epoch() / std::chrono::seconds(1);
     const std::size_t afs = cwsl_rx_group_af_size(rx, g.id);
-    g.audio.resize(g.members.size() * afs);
+    if (g.audioElems != g.members.size() * afs) {  // pinned + managed: only the demodulated columns cross PCIe
+        cwsl_host_free(g.audio);
+        g.audioElems = g.members.size() * afs;
+        g.audio = static_cast<std::int16_t*>(cwsl_host_alloc(g.audioElems * sizeof(std::int16_t)));
+        if (!g.audio) {
+            g.audioElems = 0;
+            screenPrinter->err(receiverLog() + std::string("hand-off buffer: ") + cwsl_last_error());
+            return;
+        }
+    }
     std::size_t wi = 0;
-    if (cwsl_rx_end_slot(rx, g.id, g.audio.data(), &wi) != CWSL_OK || cwsl_rx_synchronize(rx) != CWSL_OK) {
+    if (cwsl_rx_end_slot(rx, g.id, g.audio, &wi) != CWSL_OK || cwsl_rx_wait_output(rx) != CWSL_OK) {
         screenPrinter->err(receiverLog() + std::string("slot failed: ") + cwsl_last_error());  // failed slot, carry on
         g.startEpochTime = now;
         return;
@@ -119,7 +128,7 @@ inline void Receiver::finishSlot(SlotGroup& g) {
     }
     for (std::size_t m = 0; m < g.members.size(); ++m) {
         Instance* inst = g.members[m];
-        std::vector<std::int16_t> audioBuf_i16(g.audio.begin() + m * afs, g.audio.begin() + (m + 1) * afs);
+        std::vector<std::int16_t> audioBuf_i16(g.audio + m * afs, g.audio + (m + 1) * afs);
         ItemToDecode toDecode(std::move(audioBuf_i16), inst->getMode(), startTime, inst->getFrequency(),
                               static_cast<int>(inst->getId()), inst->getCwd(), inst->getTRPeriod());
         inst->getDecoderPool()->push(std::move(toDecode));  // Instance.cpp:244-245

@@ -31,6 +31,7 @@ public:
     virtual ~Receiver() {
         if (status != ReceiverStatus::FINISHED) terminate();
         if (rx) cwsl_rx_destroy(rx);
+        for (auto& g : groups) cwsl_host_free(g.audio);
     }
 
     // opens the producer and creates the GPU front-end (source/Receiver.hpp:115-176 opens the shared
@@ -99,7 +100,8 @@ private:
         float period = 0;
         std::vector<Instance*> members;
         std::uint64_t startEpochTime = 0;  // 0 = first, partial buffer -> discarded (Instance.cpp:224-227)
-        std::vector<std::int16_t> audio;   // [members][af_size]
+        std::int16_t* audio = nullptr;     // [members][af_size], pinned hand-off buffer (cwsl_host_alloc)
+        std::size_t audioElems = 0;
     };
 
     void readIQ();

@@ -112,3 +112,35 @@ def test_product_does_not_import_oracle():
                 assert "import oracle" not in txt and "from oracle" not in txt, fn
                 assert "liboracle" not in txt and "libcwsl_ref" not in txt, fn
                 assert '#include "SSBD.hpp"' not in txt and "/root/reference" not in txt, fn
+
+
+# ---- property tests (hypothesis): host arithmetic of the C ABI against the oracle restatement ----------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=150, deadline=None)
+@given(n=st.integers(0, 4000), k=st.integers(1, 16), fs=st.sampled_from([48000, 96000, 192000]),
+       afs=st.integers(2, 400000))
+def test_accepted_blocks_property(cw, port, n, k, fs, afs):
+    iq_len = k * (2 * fs // 6000)                      # any multiple of SSBD::GetInSize()
+    got = cw.accepted_blocks(n, iq_len, fs, afs)
+    assert got == port.accepted_blocks(n * iq_len, iq_len, fs // 12000, afs)
+    assert got <= n
+    if got < n:                                        # the guard tripped: one more block would not have fitted
+        assert got * (iq_len // (fs // 12000)) + iq_len > afs - 1
+
+
+@settings(max_examples=60, deadline=None)
+@given(fs=st.sampled_from([48000, 96000, 192000]), frac=st.floats(-0.5, 0.5), usb=st.booleans())
+def test_tables_property(cw, ref, fs, frac, usb):
+    f = int(frac * fs)
+    legal = abs(f) <= fs // 2 and abs(f + (6000 if usb else -6000)) <= fs // 2      # SSBD.hpp:100-103
+    if legal:
+        a, b = ref.tables(fs, f, is_usb=usb), cw.build_tables(fs, f, is_usb=usb)
+        for key in ("tone", "phase_inc"):
+            assert np.array_equal(_bits(a[key]), _bits(b[key])), (fs, f, usb, key)
+    else:
+        with pytest.raises(cw.CwslError):
+            cw.build_tables(fs, f, is_usb=usb)
+        with pytest.raises(ValueError):
+            ref.tables(fs, f, is_usb=usb)
