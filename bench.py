@@ -405,10 +405,10 @@ def run_b200(a):
                         kernel="demod_fast_kernel<16,4,128>" if a.mode == "fast" else "demod_exact_kernel<16>",
                         launch_ms=launch_ms, launches_timed=demod_launches,
                         kernel_share_of_step=demod_ms / (ms_total if ms_total > 0 else 1),
-                        peak_source="FFMA2 register-resident microbenchmark run in this process "
-                                    "(cwsl_measure_fp32_peak); MEASURED_PEAKS.json has no FP32-pipe figure. "
-                                    f"Nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; plain FFMA "
-                                    f"measured {fp32['ffma_tflops']:.1f}",
+                        peak_source="register-resident FMA microbenchmark with immediate operands run in this process "
+                                    "(cwsl_measure_fp32_peak, max of the FFMA2 and FFMA forms); MEASURED_PEAKS.json has "
+                                    "no FP32-pipe figure. Nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; "
+                                    f"measured FFMA2 {fp32['ffma2_tflops']:.1f}, scalar FFMA {fp32['ffma_tflops']:.1f}",
                         algorithmic="134 flop per channel-sample (SURVEY.md 8d) x channels x IQ samples per launch; "
                                     "frac can exceed 1: the kernel folds the symmetric taps and executes fewer "
                                     "multiplies than the direct form the 134 counts (see 'executed')",
