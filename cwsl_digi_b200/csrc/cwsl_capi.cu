@@ -353,6 +353,8 @@ int process_group(cwsl_rx* rx, Group& g) {
     p.audio = g.d_audio;
     p.af_stride = g.af_stride;
     p.maxbits = g.d_maxbits;
+    // the post stream may still be normalising / copying the previous slot out of the buffers this launch rewrites
+    if (rx->d2h_pending) CK(cudaStreamWaitEvent(rx->stream, rx->ev_d2h_done, 0));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (rx->timing) {
         e0 = get_event(rx);
@@ -686,18 +688,23 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
     q.out = g->d_out;
     q.factor_out = g->d_factor;
     q.max_out = g->d_maxval;
+    // Everything after the demodulation -- the HBM-bound normalise/quantise pass, the max reset and the copy to
+    // the host -- runs on the receiver's private post stream behind an event, so it overlaps the FMA-bound
+    // demodulation of whatever is queued next on `stream` (other receivers sharing it, or this receiver's other
+    // groups). Work of successive slots is ordered on the post stream itself; the next demodulation of THIS
+    // receiver waits for ev_d2h_done (process_group), because it rewrites the float audio and the max.
+    CK(cudaEventRecord(rx->ev_out_ready, rx->stream));
+    CK(cudaStreamWaitEvent(rx->copy_stream, rx->ev_out_ready, 0));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (rx->timing) {
         e0 = get_event(rx);
         e1 = get_event(rx);
-        CK(cudaEventRecord(e0, rx->stream));
+        CK(cudaEventRecord(e0, rx->copy_stream));
     }
-    // the previous slot's device->host copy (on the copy stream) may still be reading an int16 buffer
-    if (rx->d2h_pending) CK(cudaStreamWaitEvent(rx->stream, rx->ev_d2h_done, 0));
-    CK(cwsl::launch_quantise(q, rx->stream));
-    CK(cwsl::launch_clear_u32(g->d_maxbits, C, rx->stream));  // next slot starts from max|x| = 0
+    CK(cwsl::launch_quantise(q, rx->copy_stream));
+    CK(cwsl::launch_clear_u32(g->d_maxbits, C, rx->copy_stream));  // next slot starts from max|x| = 0
     if (rx->timing) {
-        CK(cudaEventRecord(e1, rx->stream));
+        CK(cudaEventRecord(e1, rx->copy_stream));
         rx->ev_quant.emplace_back(e0, e1);
     }
     if (out_i16) {
@@ -726,10 +733,6 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
                 }
             }
         }
-        // The copy runs on the receiver's private copy stream, behind an event: the kernels of whatever is queued
-        // next on `stream` (this receiver's next slot, or other receivers sharing the stream) overlap it.
-        CK(cudaEventRecord(rx->ev_out_ready, rx->stream));
-        CK(cudaStreamWaitEvent(rx->copy_stream, rx->ev_out_ready, 0));
         if (cols >= g->af_size) {
             CK(cudaMemcpyAsync(out_i16, g->d_out, (size_t)C * g->af_size * sizeof(int16_t), cudaMemcpyDeviceToHost,
                                rx->copy_stream));
@@ -737,9 +740,9 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
             CK(cudaMemcpy2DAsync(out_i16, g->af_size * sizeof(int16_t), g->d_out, g->af_size * sizeof(int16_t),
                                  cols * sizeof(int16_t), C, cudaMemcpyDeviceToHost, rx->copy_stream));
         }
-        CK(cudaEventRecord(rx->ev_d2h_done, rx->copy_stream));
-        rx->d2h_pending = true;
     }
+    CK(cudaEventRecord(rx->ev_d2h_done, rx->copy_stream));
+    rx->d2h_pending = true;
     if (write_index) *write_index = (size_t)g->processed;
     g->last_write_index = (size_t)g->processed;
     g->have_result = true;
@@ -762,7 +765,7 @@ int cwsl_rx_copy_device_audio(cwsl_rx_t* rx, int group, int channel, int16_t* d_
     if (channel < 0 || channel >= (int)g->ch.size()) return fail(CWSL_ERR_INVALID, "bad channel %d", channel);
     DeviceGuard dg(rx->device);
     CK(cudaMemcpyAsync(d_dst, g->d_out + (size_t)channel * g->af_size, g->af_size * sizeof(int16_t),
-                       cudaMemcpyDeviceToDevice, rx->stream));
+                       cudaMemcpyDeviceToDevice, rx->copy_stream));  // ordered behind the slot's quantise
     return CWSL_OK;
 }
 
@@ -773,6 +776,7 @@ int cwsl_rx_read_float_audio(cwsl_rx_t* rx, int group, int channel, float* out) 
     if (channel < 0 || channel >= (int)g->ch.size()) return fail(CWSL_ERR_INVALID, "bad channel %d", channel);
     DeviceGuard dg(rx->device);
     CK(cudaStreamSynchronize(rx->stream));
+    CK(cudaStreamSynchronize(rx->copy_stream));
     std::memset(out, 0, g->af_size * sizeof(float));
     CK(cudaMemcpy(out, g->d_audio + (size_t)channel * g->af_stride, g->last_write_index * sizeof(float),
                   cudaMemcpyDeviceToHost));
@@ -786,6 +790,7 @@ int cwsl_rx_channel_stats(cwsl_rx_t* rx, int group, int channel, float* max_val,
     if (channel < 0 || channel >= (int)g->ch.size()) return fail(CWSL_ERR_INVALID, "bad channel %d", channel);
     DeviceGuard dg(rx->device);
     CK(cudaStreamSynchronize(rx->stream));
+    CK(cudaStreamSynchronize(rx->copy_stream));
     if (max_val) CK(cudaMemcpy(max_val, g->d_maxval + channel, sizeof(float), cudaMemcpyDeviceToHost));
     if (factor) CK(cudaMemcpy(factor, g->d_factor + channel, sizeof(float), cudaMemcpyDeviceToHost));
     return CWSL_OK;
@@ -816,6 +821,7 @@ int cwsl_rx_kernel_times(cwsl_rx_t* rx, float* demod_ms, float* quant_ms, int* d
     if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
     DeviceGuard dg(rx->device);
     CK(cudaStreamSynchronize(rx->stream));
+    CK(cudaStreamSynchronize(rx->copy_stream));
     float dsum = 0, qsum = 0;
     for (auto& pr : rx->ev_demod) {
         float ms = 0;
