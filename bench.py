@@ -405,6 +405,10 @@ def run_b200(a):
                         kernel="demod_fast_kernel<16,4,128>" if a.mode == "fast" else "demod_exact_kernel<16>",
                         launch_ms=launch_ms, launches_timed=demod_launches,
                         kernel_share_of_step=demod_ms / (ms_total if ms_total > 0 else 1),
+                        share_note="demod launch time / timed region, CUDA events. The normalise+quantise pass of "
+                                   "receiver r (3.6 % of the kernel time when serialised, profiles/r1_launches_v3.csv) "
+                                   "runs on the receiver's post stream and overlaps the demodulation of receiver r+1, "
+                                   "so the demod kernel covers ~100 % of the region",
                         peak_source="register-resident FMA microbenchmark with immediate operands run in this process "
                                     "(cwsl_measure_fp32_peak, max of the FFMA2 and FFMA forms); MEASURED_PEAKS.json has "
                                     "no FP32-pipe figure. Nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; "
