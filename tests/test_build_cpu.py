@@ -41,7 +41,7 @@ def test_exact_kernels_have_no_fused_multiply_add(cw):
 
 def test_fast_kernel_is_ffma2_tma_and_spill_free(cw):
     funcs = _sass(cw)
-    fast = {k: v for k, v in funcs.items() if "demod_fast_kernelILi16" in k and k.endswith("Lb0EEEvNS_11DemodLaunchEjj")}
+    fast = {k: v for k, v in funcs.items() if "demod_fast_kernelILi16ELi4ELi128ELi2ELb0E" in k}
     assert len(fast) == 1                               # the production instantiation (no register prefetch)
     (name, body), = fast.items()
     ops = _ops(body)
