@@ -18,35 +18,35 @@
 #define RX_SAMPLE_RATE 12000
 
 typedef struct dec_data {
-    int ipc[3];
-    float ss[184 * NSMAX];
+    int ipc[3];                      // [0] nzhsym, [1] istart, [2] idone handshake words
+    float ss[184 * NSMAX];           // symbol spectra (jt9 fills/reads; zeroed here)
     float savg[NSMAX];
     float sred[5760];
-    short int d2[NTMAX * RX_SAMPLE_RATE];
-    struct {
-        int nutc;          // UTC as integer, HHMM
-        bool ndiskdat;     // true ==> data read from *.wav file
-        int ntrperiod;     // TR period (seconds)
-        int nQSOProgress;  // QSO state machine state
-        int nfqso;         // User-selected QSO freq (kHz)
-        int nftx;          // Transmit audio offset where replies might be expected
-        bool newdat;       // true ==> new data, must do long FFT
-        int npts8;         // npts for c0() array
-        int nfa;           // Low decode limit (Hz)
-        int nfSplit;       // JT65 | JT9 split frequency
-        int nfb;           // High decode limit (Hz)
-        int ntol;          // +/- decoding range around fQSO (Hz)
+    short int d2[NTMAX * RX_SAMPLE_RATE];  // 12 kHz int16 audio: where the front-end's output goes
+    struct {                         // field order and types are the ABI of lib/jt9com.f90 -- do not reorder
+        int nutc;                    // HHMM
+        bool ndiskdat;               // data came from a .wav file
+        int ntrperiod;               // T/R period, s
+        int nQSOProgress;
+        int nfqso;                   // QSO audio frequency
+        int nftx;
+        bool newdat;                 // new data: run the long FFT
+        int npts8;
+        int nfa;                     // lowest decode frequency, Hz
+        int nfSplit;
+        int nfb;                     // highest decode frequency, Hz
+        int ntol;                    // search range around nfqso, Hz
         int kin;
-        int nzhsym;
+        int nzhsym;                  // half-symbol count that triggers the decode
         int nsubmode;
         bool nagain;
-        int ndepth;
+        int ndepth;                  // decode depth 1..3
         bool lft8apon;
         bool lapcqonly;
         bool ljt65apon;
         int napwid;
         int ntxmode;
-        int nmode;
+        int nmode;                   // 8 FT8, 5 FT4, 65 JT65, 66 Q65, 240 FST4, 241 FST4W
         int minw;
         bool nclearave;
         int minSync;
