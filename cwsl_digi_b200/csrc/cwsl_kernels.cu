@@ -742,12 +742,19 @@ cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
     if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
     // CWSL_EXACT_SHAPE=256x2 selects 256-thread CTAs, 2 per SM (16 warps/SM); default 128x3 (12 warps/SM, cheaper
     // barriers: measured below)
-    static const bool big = [] {
+    static const int shape = [] {
         const char* e = std::getenv("CWSL_EXACT_SHAPE");
-        return e && std::string(e) == "256x2";
+        if (e && std::string(e) == "256x2") return 1;
+        if (e && std::string(e) == "64x6") return 2;
+        if (e && std::string(e) == "64x5") return 3;
+        return 0;
     }();
     switch (p.block_size) {
-        case 16: return big ? launch_exact_t<16, 256, 2, 24>(p, s) : launch_exact_t<16, 128, 3, 32>(p, s);
+        case 16:
+            if (shape == 1) return launch_exact_t<16, 256, 2, 24>(p, s);
+            if (shape == 2) return launch_exact_t<16, 64, 6, 16>(p, s);
+            if (shape == 3) return launch_exact_t<16, 64, 5, 32>(p, s);
+            return launch_exact_t<16, 128, 3, 32>(p, s);
         case 8: return launch_exact_t<8, 128, 3, 32>(p, s);
         case 4: return launch_exact_t<4, 128, 3, 32>(p, s);
         default: return cudaErrorInvalidValue;
