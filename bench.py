@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                       "-lms", "25", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                       stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.p = None
