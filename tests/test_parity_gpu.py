@@ -176,6 +176,36 @@ def test_empty_slot_is_all_zero(gpu):
         assert mx == 0.0 and fac == np.float32(np.float32(32767.0) / np.float32(1.0)) * np.float32(0.9)
 
 
+@pytest.mark.parametrize("kind", ["zeros", "dc", "huge", "tiny", "impulse"])
+def test_degenerate_inputs(gpu, ref, kind):
+    """All-zero, DC, very large, denormal-scale and single-impulse IQ: EXACT stays bit-identical (signed zeros
+    included), FAST stays within its bars (or is exactly zero where the reference is)."""
+    cw = gpu
+    fs, iq_len = 192000, 2048
+    n = 12 * iq_len
+    iq = np.zeros(2 * n, np.float32)
+    if kind == "dc":
+        iq[0::2], iq[1::2] = 1234.5, -987.25
+    elif kind == "huge":
+        iq[:] = synth.receiver_iq(n, fs, [-26000], receiver=8, tones_per_channel=1) * np.float32(1e12)
+    elif kind == "tiny":
+        iq[:] = synth.receiver_iq(n, fs, [-26000], receiver=8, tones_per_channel=1) * np.float32(1e-30)
+    elif kind == "impulse":
+        iq[2 * 5000] = 1.0e4
+    chans = [(-26000, 0.9), (0, 0.2)]
+    want = [ref.slot(fs, f, iq, iq_len, sc, af_size(15)) for f, sc in chans]
+    out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, chans, iq, cw.MODE_EXACT)
+    check_exact(out, raw, wi, stats, want)
+    out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, chans, iq, cw.MODE_FAST)
+    for c, o in enumerate(want):
+        d = np.abs(out[c].astype(np.int32) - o["i16"].astype(np.int32))
+        assert d.max() <= FAST_MAX_LSB
+        if kind == "zeros":
+            assert not out[c].any() and not raw[c].any()
+        elif kind != "tiny":                              # (denormal products: the int16 bar is the meaningful one)
+            assert resid_db(raw[c][:wi], o["raw"][:wi]) <= -FAST_MIN_RESID_DB
+
+
 def test_af_buffer_full_guard(gpu, ref):
     # FT4 buffer (150000 samples) fed 13 s of IQ: the guard (Instance.cpp:268-271) drops the excess
     cw = gpu
