@@ -187,9 +187,22 @@ void free_group_device(Group& g) {
     g.phase_keys.clear();
 }
 
-// Upload tables, build missing phase tables, allocate audio buffers. Idempotent.
+int commit_impl(cwsl_rx* rx);
+
+// Upload tables, build missing phase tables, allocate audio buffers. Idempotent; on failure everything this
+// attempt allocated is released again, so a later call starts from scratch instead of leaking.
 int commit(cwsl_rx* rx) {
     if (rx->committed) return CWSL_OK;
+    const int rc = commit_impl(rx);
+    if (rc != CWSL_OK) {
+        const std::string msg = g_last_error;  // free_group_device must not clobber the reason
+        for (Group& g : rx->groups) free_group_device(g);
+        g_last_error = msg;
+    }
+    return rc;
+}
+
+int commit_impl(cwsl_rx* rx) {
     if (rx->groups.empty()) return fail(CWSL_ERR_STATE, "no slot group defined");
     // One-time setup of this receiver allocates GBs of device memory. Do it on a quiet device: with more than
     // ~8 receivers on private non-blocking streams, cudaMalloc overlapping other receivers' running kernels
@@ -608,6 +621,8 @@ int cwsl_rx_add_channel(cwsl_rx_t* rx, int group, int32_t demod_freq_hz, int is_
     ch.scale = scale;
     if (!cwsl::nco_tables(rx->geo, demod_freq_hz, is_usb != 0, &ch.nco))
         return fail(CWSL_ERR_INVALID, "Signal outside of band (demod %d Hz at Fs %u)", demod_freq_hz, rx->fs);
+    if (g->ch.size() >= 65535)  // channels are a grid dimension of the normalise/quantise launch
+        return fail(CWSL_ERR_INVALID, "at most 65535 channels per slot group");
     g->ch.push_back(std::move(ch));
     return (int)g->ch.size() - 1;
 }
