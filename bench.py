@@ -346,8 +346,6 @@ def run_b200(a):
             step_e2e()
         barrier()
         t0 = time.perf_counter()
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ev0.record(torch.cuda.current_stream())
         for _ in range(a.steps):
             step_e2e()
         torch.cuda.synchronize()
