@@ -37,10 +37,10 @@ FS, IQ_LEN, PERIOD = 192000, 2048, 15.0
 N_RECEIVERS, N_CHANNELS = 64, 1024
 FLOP_PER_CH_SAMPLE = 134.0          # SURVEY.md section 8d (mix 6 + 32 taps x 4): the ALGORITHMIC work
 # What demod_fast_kernel<16,4,128> actually issues on the FMA pipe per SSBD block (16 ch-samples), from its SASS
-# (cuobjdump, 2x-unrolled loop: 514 FFMA2 + 157 FADD2 + 128 FMUL2 per 2 blocks): the symmetric taps are folded
-# (h[j] = h[512-j]) so fewer multiplies are executed than the algorithm counts. Each packed instruction = 2 lanes
-# x 2 flop-slots; a segment of 3 tiles (1536 blocks) recomputes a 32-block overlap once.
-FAST_PIPE_INSTR_PER_BLOCK = 399.5
+# (cuobjdump, fully unrolled 4-block row: 1028 FFMA2 + 280 FADD2 + 256 FMUL2, exchange adds included): the symmetric
+# taps are folded (h[j] = h[512-j]) so fewer multiplies are executed than the algorithm counts. Each packed
+# instruction = 2 lanes x 2 flop-slots; a segment of 3 tiles (1536 blocks) recomputes a 32-block overlap once.
+FAST_PIPE_INSTR_PER_BLOCK = 391.0
 FAST_TILE_OVERHEAD = 1536.0 / 1504.0
 METRIC, UNIT = "channel-Msamples/s (IQ in x decoders)", "ch-Msamples/s"
 

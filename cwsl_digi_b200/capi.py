@@ -29,7 +29,8 @@ class CwslError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libcwsl_b200.so")
+    # CWSL_B200_LIB selects another build of the same library (A/B experiments); default: the in-tree build
+    return os.environ.get("CWSL_B200_LIB") or os.path.join(_HERE, "libcwsl_b200.so")
 
 
 def build_library(quiet: bool = True) -> str:
