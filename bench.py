@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 FS, IQ_LEN, PERIOD = 192000, 2048, 15.0
 N_RECEIVERS, N_CHANNELS = 64, 1024
 FLOP_PER_CH_SAMPLE = 134.0          # SURVEY.md section 8d (mix 6 + 32 taps x 4): the ALGORITHMIC work
-# What demod_fast_kernel<16,4,128> actually issues on the FMA pipe per SSBD block (16 ch-samples), from its SASS
+# What demod_fast_kernel<16,4,128,2> actually issues on the FMA pipe per SSBD block (16 ch-samples), from its SASS
 # (cuobjdump, fully unrolled 4-block row: 1028 FFMA2 + 280 FADD2 + 256 FMUL2, exchange adds included): the symmetric
 # taps are folded (h[j] = h[512-j]) so fewer multiplies are executed than the algorithm counts. Each packed
 # instruction = 2 lanes x 2 flop-slots; a segment of 3 tiles (1536 blocks) recomputes a 32-block overlap once.
@@ -400,7 +400,7 @@ def run_b200(a):
             pass
         roofline = dict(bound="fp32_fma_pipe", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
                         frac=achieved_tf / peak_tf, traffic=traffic,
-                        kernel="demod_fast_kernel<16,4,128>" if a.mode == "fast" else "demod_exact_kernel<16>",
+                        kernel="demod_fast_kernel<16,4,128,2>" if a.mode == "fast" else "demod_exact_kernel<16>",
                         launch_ms=launch_ms, launches_timed=demod_launches,
                         kernel_share_of_step=demod_ms / (ms_total if ms_total > 0 else 1),
                         share_note="demod launch time / timed region, CUDA events. The normalise+quantise pass of "
