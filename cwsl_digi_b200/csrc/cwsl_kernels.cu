@@ -570,7 +570,8 @@ struct ExactCfg {
     static constexpr int kRowStride = kRowBytes + 16;   // conflict-free per-thread LDS.128
     static constexpr int kDStride = 33;                 // float2 per D row (32 + 1 pad: conflict-free both ways)
     static constexpr size_t kXBytes = (size_t)NT * kRowStride;
-    static constexpr size_t kDBytes = (size_t)NT * kDStride * 8;
+    static constexpr int kZeroRows = 31;                // D rows -31..-1: fresh-SSBD / previous-tile history, all +0
+    static constexpr size_t kDBytes = (size_t)(NT + kZeroRows) * kDStride * 8;
     static constexpr size_t kToneBytes = (size_t)G * BS * 8;
     static constexpr size_t kCarryBytes = (size_t)G * 31 * 8;
     static constexpr size_t kSmem = kXBytes + kDBytes + kToneBytes + kCarryBytes + 16;
@@ -588,9 +589,11 @@ template <int BS, int NT, int CTAS, int G>
 __global__ void __launch_bounds__(NT, CTAS)
     demod_exact_tiled_kernel(DemodLaunch p, uint32_t ch_per_cta, uint32_t tiles_per_seg) {
     using Cfg = ExactCfg<BS, NT, G>;
+    static_assert(NT >= 62, "the carry loop assumes its source rows are never before the slot");
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* xs = smem;
-    float2* D = reinterpret_cast<float2*>(smem + Cfg::kXBytes);
+    float2* D0 = reinterpret_cast<float2*>(smem + Cfg::kXBytes);
+    float2* D = D0 + (size_t)Cfg::kZeroRows * Cfg::kDStride;  // row 0 of the tile; rows -31..-1 stay +0 forever
     float2* tone_s = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kDBytes);
     float2* carry_s = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kDBytes + Cfg::kToneBytes);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kDBytes + Cfg::kToneBytes + Cfg::kCarryBytes);
@@ -610,6 +613,7 @@ __global__ void __launch_bounds__(NT, CTAS)
         fence_mbar_init();
     }
     for (uint32_t i = t; i < nch * BS; i += NT) tone_s[i] = p.tone[(size_t)c0 * BS + i];
+    for (int i = t; i < Cfg::kZeroRows * Cfg::kDStride; i += NT) D0[i] = make_float2(0.0f, 0.0f);
     __syncthreads();
 
     const float4* __restrict__ xrow = reinterpret_cast<const float4*>(xs + (size_t)t * Cfg::kRowStride);
@@ -673,16 +677,13 @@ __global__ void __launch_bounds__(NT, CTAS)
             // y[b] = sum over tap rows n ascending of D[b-31+n][n]; rows before this tile are in the carry
             float2 w = make_float2(0.0f, 0.0f);
             if (!first_tile && t < 31) w = carry_s[ci * 31 + t];
-            // a row that is outside the slot (k < 0: fresh-SSBD history) is never added by the reference, so it
-            // must not be added here either (adding +0 could flip a -0): rows < 0 only occur in the first tile
-            const int n_lo = max(0, 31 - t);  // first tap row whose source block lies in this tile
+            // No predicates: a source row that lies before this tile (t - 31 + n < 0) is one of the 31 zero rows
+            // in front of D, a row outside the slot (k < 0, fresh-SSBD history) was written as +0 by its thread.
+            // Adding +0 is exact here: a float sum that starts from +0 (or from a carry that did) can never be
+            // -0 under round-to-nearest, and x + (+0) == x for every other x. (The per-row predicates these
+            // zeros replace cost 14 % of the kernel's issue slots.)
 #pragma unroll
-            for (int n = 0; n < 32; ++n) {
-                if (n >= n_lo) {
-                    const int64_t src_k = kt0 + t - 31 + n;
-                    if (src_k >= 0) w = fadd2(w, D[(size_t)(t - 31 + n) * Cfg::kDStride + n]);
-                }
-            }
+            for (int n = 0; n < 32; ++n) w = fadd2(w, D[((int)t - 31 + n) * Cfg::kDStride + n]);
             __syncwarp();
             // prefix owed to the next tile: output NT + j gets rows (NT + j - 31 + n) < NT, n ascending
             if (t < 31) {
@@ -690,7 +691,8 @@ __global__ void __launch_bounds__(NT, CTAS)
 #pragma unroll
                 for (int n = 0; n < 31; ++n) {
                     const int src = NT + t - 31 + n;  // tile-local row
-                    if (src < NT && kt0 + src >= 0) cs = fadd2(cs, D[(size_t)src * Cfg::kDStride + n]);
+                    // (src >= NT - 31 >= 31 and kt0 >= -31, so the source block is never before the slot)
+                    if (src < NT) cs = fadd2(cs, D[(size_t)src * Cfg::kDStride + n]);
                 }
                 carry_s[ci * 31 + t] = cs;
             }
@@ -765,12 +767,12 @@ cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
     }();
     switch (p.block_size) {
         case 16:
-            if (shape == 1) return launch_exact_t<16, 256, 2, 24>(p, s);
-            if (shape == 2) return launch_exact_t<16, 64, 6, 16>(p, s);
-            if (shape == 3) return launch_exact_t<16, 64, 5, 32>(p, s);
-            return launch_exact_t<16, 128, 3, 32>(p, s);
-        case 8: return launch_exact_t<8, 128, 3, 32>(p, s);
-        case 4: return launch_exact_t<4, 128, 3, 32>(p, s);
+            if (shape == 1) return launch_exact_t<16, 256, 1, 24>(p, s);
+            if (shape == 2) return launch_exact_t<16, 64, 5, 16>(p, s);
+            if (shape == 3) return launch_exact_t<16, 64, 4, 32>(p, s);
+            return launch_exact_t<16, 128, 3, 24>(p, s);  // 69.4 KB of shared memory per CTA
+        case 8: return launch_exact_t<8, 128, 3, 24>(p, s);
+        case 4: return launch_exact_t<4, 128, 3, 24>(p, s);
         default: return cudaErrorInvalidValue;
     }
 }
