@@ -395,12 +395,13 @@ def run_b200(a):
             hbm_peak = 6650.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "demod_fast_traffic.json")))["dram_bytes_per_launch"]
+            if a.mode == "fast":   # the exact kernel's capture (profiles/demod_exact_traffic.json) is a 256-channel launch
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "demod_fast_traffic.json")))["dram_bytes_per_launch"]
         except Exception:  # noqa: BLE001
             pass
         roofline = dict(bound="fp32_fma_pipe", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
                         frac=achieved_tf / peak_tf, traffic=traffic,
-                        kernel="demod_fast_kernel<16,4,128,2>" if a.mode == "fast" else "demod_exact_kernel<16>",
+                        kernel="demod_fast_kernel<16,4,128,2>" if a.mode == "fast" else "demod_exact_tiled_kernel<16,128,3,24>",
                         launch_ms=launch_ms, launches_timed=demod_launches,
                         kernel_share_of_step=demod_ms / (ms_total if ms_total > 0 else 1),
                         share_note="demod launch time / timed region, CUDA events. The normalise+quantise pass of "

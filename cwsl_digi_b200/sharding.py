@@ -3,7 +3,7 @@ station-level gather of per-slot audio. The data path itself needs no collective
 nothing (source/CWSL_DIGI.cpp:80, 115-129). torch.distributed is plumbing only."""
 from __future__ import annotations
 
-from typing import List, Sequence
+from typing import List, Sequence, Tuple
 
 
 def receivers_of_rank(n_receivers: int, rank: int, world: int) -> List[int]:
@@ -15,6 +15,30 @@ def receivers_of_rank(n_receivers: int, rank: int, world: int) -> List[int]:
 
 def owner_of_receiver(receiver: int, world: int) -> int:
     return receiver % world
+
+
+def channel_slices_of_rank(n_receivers: int, n_channels: int, rank: int, world: int,
+                           granule: int = 32) -> List[Tuple[int, int, int]]:
+    """Secondary partition for a station with fewer receivers than GPUs: the ranks are
+    dealt to the receivers round-robin and the ranks of one receiver split its channel list into contiguous
+    slices (multiples of ``granule`` channels, the fast kernel's channel group, except the last). Every rank
+    of a receiver is fed the same IQ; channels are independent (one SSBD each, source/Instance.cpp:186), so
+    the concatenated slices equal the unsplit result bit for bit. With world <= n_receivers this degrades
+    to receivers_of_rank with full slices. Returns [(receiver, ch_begin, ch_end), ...]."""
+    if world <= 0 or not (0 <= rank < world) or granule <= 0:
+        raise ValueError("bad rank/world")
+    if n_receivers <= 0 or n_channels <= 0:
+        return []
+    if world <= n_receivers:
+        return [(r, 0, n_channels) for r in receivers_of_rank(n_receivers, rank, world)]
+    receiver = rank % n_receivers
+    peers = list(range(receiver, world, n_receivers))         # ranks serving this receiver
+    granules = -(-n_channels // granule)
+    k = peers.index(rank)
+    g0 = granules * k // len(peers)
+    g1 = granules * (k + 1) // len(peers)
+    lo, hi = min(g0 * granule, n_channels), min(g1 * granule, n_channels)
+    return [(receiver, lo, hi)] if hi > lo else []
 
 
 def gather_slot_audio(local: Sequence, dst: int = 0):

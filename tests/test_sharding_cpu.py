@@ -25,6 +25,24 @@ def test_partition_covers_every_receiver_once():
         sharding.receivers_of_rank(8, 2, 2)
 
 
+def test_channel_slices_cover_every_channel_once():
+    for n_rx, n_ch, w in [(1, 1024, 8), (1, 7, 8), (2, 100, 8), (3, 1000, 8), (8, 56, 8), (64, 1024, 8), (1, 33, 2),
+                          (5, 64, 4), (1, 1, 1)]:
+        seen = {}
+        for r in range(w):
+            for rx, lo, hi in sharding.channel_slices_of_rank(n_rx, n_ch, r, w):
+                assert 0 <= lo < hi <= n_ch
+                assert lo % 32 == 0
+                for c in range(lo, hi):
+                    assert (rx, c) not in seen
+                    seen[(rx, c)] = r
+        assert len(seen) == n_rx * n_ch
+    # fewer receivers than ranks: every rank of a big receiver gets work, slices are balanced to a granule
+    sizes = [sum(hi - lo for _, lo, hi in sharding.channel_slices_of_rank(1, 1024, r, 8)) for r in range(8)]
+    assert sizes == [128] * 8
+    assert sharding.channel_slices_of_rank(64, 1024, 3, 8) == [(r, 0, 1024) for r in range(3, 64, 8)]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
