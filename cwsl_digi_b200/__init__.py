@@ -5,8 +5,8 @@ The product is the C-ABI shared library ``libcwsl_b200.so`` (include/cwsl_b200.h
 is only a thin ctypes binding used by the tests and bench.py; it contains no compute and no
 CPU fallback: if the library is missing it raises.
 """
-from .capi import (CwslError, Receiver, HostBuffer, MODE_EXACT, MODE_FAST, af_size, accepted_blocks,  # noqa: F401
+from .capi import (CwslError, Receiver, HostBuffer, MODE_EXACT, MODE_FAST, MODE_STFT, af_size, accepted_blocks,  # noqa: F401
                    build_tables, ssbd_params, device_count, measure_fp32_peak, lib, lib_path, build_library)
 
-__all__ = ["CwslError", "Receiver", "HostBuffer", "MODE_EXACT", "MODE_FAST", "af_size", "accepted_blocks", "build_tables",
+__all__ = ["CwslError", "Receiver", "HostBuffer", "MODE_EXACT", "MODE_FAST", "MODE_STFT", "af_size", "accepted_blocks", "build_tables",
            "ssbd_params", "device_count", "measure_fp32_peak", "lib", "lib_path", "build_library"]

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-MODE_EXACT, MODE_FAST = 0, 1
+MODE_EXACT, MODE_FAST, MODE_STFT = 0, 1, 2
 
 # every symbol include/cwsl_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [

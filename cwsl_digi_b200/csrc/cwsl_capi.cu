@@ -61,6 +61,11 @@ struct PhaseEntry {
 std::mutex g_mu;
 std::map<PhaseKey, PhaseEntry> g_phase_cache;
 std::set<std::pair<int, uint32_t>> g_taps_uploaded;
+struct ChanDeviceTables {  // STFT channelizer: deconvolved window and FFT twiddles, one copy per device
+    float* window = nullptr;
+    float2* twiddle = nullptr;
+};
+std::map<int, ChanDeviceTables> g_chan_tables;
 
 // Managed hand-off buffers (cwsl_host_alloc): pinned, zero-initialised, and only ever written by
 // cwsl_rx_end_slot, so the library knows which columns of a destination can hold non-zero data and
@@ -98,6 +103,7 @@ struct Group {
     float* d_maxval = nullptr;
     float* d_audio = nullptr;
     int16_t* d_out = nullptr;
+    cwsl::ChanConst* d_chan = nullptr;  // STFT channelizer constants (192 kHz receivers)
     // slot state (units: SSBD blocks unless noted)
     uint64_t slot_start = 0;   // absolute index of the slot's block 0
     uint64_t processed = 0;    // slot-relative blocks already demodulated
@@ -110,6 +116,7 @@ struct Group {
 
 struct cwsl_rx {
     int device = 0;
+    ChanDeviceTables chan_tables;
     uint32_t fs = 0, iq_len = 0;
     cwsl::SsbdGeometry geo;
     uint32_t sub = 0;  // SSBD blocks per IQ block
@@ -171,6 +178,8 @@ void free_group_device(Group& g) {
     cudaFree(g.d_maxval);
     cudaFree(g.d_audio);
     cudaFree(g.d_out);
+    cudaFree(g.d_chan);
+    g.d_chan = nullptr;
     g.d_tone = nullptr;
     g.d_phase = nullptr;
     g.d_sign = g.d_scale = g.d_factor = g.d_maxval = g.d_audio = nullptr;
@@ -231,6 +240,17 @@ int commit_impl(cwsl_rx* rx) {
             CK(cwsl::upload_taps(rx->geo.block_size, h.data()));
             g_taps_uploaded.insert(key);
         }
+        if (rx->geo.block_size == 16 && !g_chan_tables.count(rx->device)) {  // STFT window + FFT twiddles, once per device
+            const std::vector<float> w = cwsl::chan_window(rx->geo, cwsl::kChanKernelWidth);
+            const std::vector<std::complex<float>> tw = cwsl::chan_twiddles();
+            ChanDeviceTables t;
+            CK(cudaMalloc(&t.window, w.size() * sizeof(float)));
+            CK(cudaMalloc(&t.twiddle, tw.size() * sizeof(float2)));
+            CK(cudaMemcpy(t.window, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(t.twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            g_chan_tables[rx->device] = t;
+        }
+        if (rx->geo.block_size == 16) rx->chan_tables = g_chan_tables[rx->device];
     }
     uint64_t max_blocks = 0;
     for (Group& g : rx->groups) {
@@ -260,6 +280,23 @@ int commit_impl(cwsl_rx* rx) {
         CK(cudaMemcpyAsync(g.d_sign, sign.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
         CK(cudaMemcpyAsync(g.d_scale, scale.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
         CK(cudaMemsetAsync(g.d_maxbits, 0, C * sizeof(unsigned), rx->stream));
+        std::vector<cwsl::ChanConst> cconst;
+        if (BS == 16) {  // STFT channelizer constants (CWSL_MODE_STFT)
+            cconst.resize(C);
+            for (uint32_t c = 0; c < C; ++c) {
+                const cwsl::ChanChannel cc = cwsl::chan_channel(rx->geo, g.ch[c].nco, cwsl::kChanKernelWidth, cwsl::kChanTaps);
+                cconst[c].q0 = cc.q0;
+                cconst[c].sign = g.ch[c].nco.sign;
+                cconst[c].rot[0] = cc.rot.real();
+                cconst[c].rot[1] = cc.rot.imag();
+                for (int i = 0; i < cwsl::kChanTaps; ++i) cconst[c].wgt[i] = cc.wgt[i];
+                cconst[c].pinc[0] = g.ch[c].nco.phase_inc.real();
+                cconst[c].pinc[1] = g.ch[c].nco.phase_inc.imag();
+                cconst[c].pad[0] = cconst[c].pad[1] = 0.0f;
+            }
+            CK(cudaMalloc(&g.d_chan, C * sizeof(cwsl::ChanConst)));
+            CK(cudaMemcpyAsync(g.d_chan, cconst.data(), C * sizeof(cwsl::ChanConst), cudaMemcpyHostToDevice, rx->stream));
+        }
         CK(cudaStreamSynchronize(rx->stream));  // host vectors go out of scope
 
         // phase tables: one per distinct (Fs, demodFreq, sideband, length), shared process-wide
@@ -344,6 +381,16 @@ uint64_t slot_target_blocks(const cwsl_rx* rx, const Group& g) {
     return (uint64_t)acc * rx->sub;
 }
 
+// CWSL_MODE_STFT uses the channelizer from this many channels per slot group on (below it the direct FAST kernel
+// is cheaper: the FFT per hop costs about as much as 24 directly filtered channels). CWSL_STFT_MIN_CHANNELS overrides.
+uint32_t stft_min_channels() {
+    static const uint32_t v = [] {
+        const char* e = std::getenv("CWSL_STFT_MIN_CHANNELS");
+        return e ? (uint32_t)std::max(1, std::atoi(e)) : 48u;
+    }();
+    return v;
+}
+
 int process_group(cwsl_rx* rx, Group& g) {
     const uint64_t target = slot_target_blocks(rx, g);
     if (target <= g.processed) return CWSL_OK;
@@ -384,6 +431,22 @@ int process_group(cwsl_rx* rx, Group& g) {
             CK(cwsl::launch_demod_exact_gather(p, rx->stream));
         else
             CK(cwsl::launch_demod_exact(p, rx->stream));
+    }
+    else if (rx->mode == CWSL_MODE_STFT && p.block_size == 16 && p.n_channels >= stft_min_channels()) {
+        // big channel groups: one FFT per hop shared by all channels, <= kChanMaxChannels channels per launch
+        for (uint32_t c0 = 0; c0 < p.n_channels; c0 += cwsl::kChanMaxChannels) {
+            cwsl::DemodLaunch q = p;
+            q.n_channels = std::min<uint32_t>(cwsl::kChanMaxChannels, p.n_channels - c0);
+            q.phase = p.phase + c0;
+            q.sign = p.sign + c0;
+            q.audio = p.audio + (size_t)c0 * p.af_stride;
+            q.maxbits = p.maxbits + c0;
+            cwsl::ChanLaunch c;
+            c.window = rx->chan_tables.window;
+            c.twiddle = rx->chan_tables.twiddle;
+            c.consts = g.d_chan + c0;
+            CK(cwsl::launch_demod_chan(q, c, rx->stream));
+        }
     }
     else
         CK(cwsl::launch_demod_fast(p, rx->stream));
@@ -573,7 +636,7 @@ void cwsl_rx_destroy(cwsl_rx_t* rx) {
 }
 
 int cwsl_rx_set_mode(cwsl_rx_t* rx, int mode) {
-    if (!rx || (mode != CWSL_MODE_EXACT && mode != CWSL_MODE_FAST)) return fail(CWSL_ERR_INVALID, "bad mode %d", mode);
+    if (!rx || (mode != CWSL_MODE_EXACT && mode != CWSL_MODE_FAST && mode != CWSL_MODE_STFT)) return fail(CWSL_ERR_INVALID, "bad mode %d", mode);
     rx->mode = mode;
     return CWSL_OK;
 }

@@ -1,0 +1,330 @@
+// STFT channelizer form of the receive chain (FAST-tolerance mode CWSL_MODE_STFT, big channel groups).
+//
+// The reference evaluates, per channel c and output sample b (source/SSBD.hpp:160-183, gather form in
+// SURVEY.md section 8 a4),
+//     y_c[b] = sum_{j<512} x[16(b-31)+j] * h[j] * LO_c[16(b-31)+j],     LO_c[16k+m] = P_c[k] * tone_c[m]
+// i.e. a 512-tap FIR at a 16-sample hop behind a per-channel NCO. Within one 512-sample window the NCO is a pure
+// exponential to ~1e-6 (P_c[k+n] = P_c[k] e^{i n Theta_c} up to float rounding, tone_c[m] = e^{i m Theta_c/16}
+// up to the rounding of its float angle), so
+//     y_c[b] = P_c[b] * e^{-i 496 w_c} * W_b(w_c),     W_b(w) = sum_j x[16(b-31)+j] h[j] e^{i w j},   w_c = Theta_c/16
+// and W_b is the DTFT of ONE windowed segment that all channels of the receiver share. The kernel computes it
+// once per hop on a 1024-point grid (zero-padded FFT, oversampling 2) and every channel reads its own frequency
+// off that grid with a W-tap Kaiser-Bessel interpolation (the type-2 non-uniform FFT: the window is pre-divided
+// by the kernel's transform). P_c[b] is still the reference's own drifting float phase recurrence (phase table),
+// so the NCO drift (|P| = 1.0004 after one FT8 slot) is reproduced; only the *within-window* deviation from a pure
+// exponential is dropped. Measured against the reference chain (tools/chan_proto.py, tests): residual <= -120 dB
+// with W = 7/8, <= 1 int16 LSB. Per channel-sample this costs ~1.5 FMA-pipe instructions instead of 24 (folded
+// direct form), which moves the path from the FP32 pipe to shared-memory/HBM bandwidth.
+//
+// One CTA = HB consecutive hops x all channels of the launch. Per batch:
+//   1. stage the (HB+31)*16 IQ samples of the batch into shared memory (zero history before the slot start,
+//      source/Instance.cpp:251),
+//   2. one warp per hop: 1024-point FFT as 32 x 32 (two register-resident radix-2 DIF 32-point passes, one
+//      shared-memory transpose, in place in the hop's spectrum buffer); window, inter-pass twiddles and the
+//      centring rotation i^q come from small L1-resident tables,
+//   3. every thread walks channels: W-tap real-weight interpolation of the complex bins (FFMA2), times
+//      rot_c * P_c[b], Weaver select (source/SSBD.hpp:132-135), max|x|, float4 audio stores.
+// CTAs stride over the batches of the launch and keep per-channel max|x| in shared memory (one atomicMax per
+// channel per CTA at the end).
+#include "cwsl_kernels.hpp"
+#include "cwsl_ptx.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
+
+namespace cwsl {
+
+namespace {
+
+constexpr int kN = 1024;         // FFT size (512-tap window, oversampling 2)
+constexpr int kL = 512;          // window length = FiltOrder at 192 kHz
+constexpr int kHopStride = 1056; // float2 per hop buffer: 32 rows of 33 during the transpose, 1024 bins after
+
+// W32^k = exp(-2 pi i k / 32), k = 0..15
+__device__ __forceinline__ float2 mul_w32(float2 d, int k) {
+    constexpr float c1 = 0.98078528040323044913f, s1 = 0.19509032201612826785f;
+    constexpr float c2 = 0.92387953251128675613f, s2 = 0.38268343236508977173f;
+    constexpr float c3 = 0.83146961230254523708f, s3 = 0.55557023301960222474f;
+    constexpr float c4 = 0.70710678118654752440f;
+    switch (k) {
+        case 0: return d;
+        case 1: return make_float2(d.x * c1 + d.y * s1, d.y * c1 - d.x * s1);
+        case 2: return make_float2(d.x * c2 + d.y * s2, d.y * c2 - d.x * s2);
+        case 3: return make_float2(d.x * c3 + d.y * s3, d.y * c3 - d.x * s3);
+        case 4: return make_float2((d.x + d.y) * c4, (d.y - d.x) * c4);
+        case 5: return make_float2(d.x * s3 + d.y * c3, d.y * s3 - d.x * c3);
+        case 6: return make_float2(d.x * s2 + d.y * c2, d.y * s2 - d.x * c2);
+        case 7: return make_float2(d.x * s1 + d.y * c1, d.y * s1 - d.x * c1);
+        case 8: return make_float2(d.y, -d.x);
+        case 9: return make_float2(d.y * c1 - d.x * s1, -(d.x * c1 + d.y * s1));
+        case 10: return make_float2(d.y * c2 - d.x * s2, -(d.x * c2 + d.y * s2));
+        case 11: return make_float2(d.y * c3 - d.x * s3, -(d.x * c3 + d.y * s3));
+        case 12: return make_float2((d.y - d.x) * c4, -(d.x + d.y) * c4);
+        case 13: return make_float2(d.y * s3 - d.x * c3, -(d.x * s3 + d.y * c3));
+        case 14: return make_float2(d.y * s2 - d.x * c2, -(d.x * s2 + d.y * c2));
+        default: return make_float2(d.y * s1 - d.x * c1, -(d.x * s1 + d.y * c1));
+    }
+}
+
+__host__ __device__ constexpr int bitrev5(int i) {
+    return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+}
+
+// In-register 32-point forward DFT, radix-2 decimation in frequency; X[bitrev5(i)] is left in v[i].
+// UPPER_ZERO: v[16..31] are known zeros on entry (the zero-padded half of the window).
+template <bool UPPER_ZERO>
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+    if constexpr (UPPER_ZERO) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k + 16] = mul_w32(v[k], k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float2 a = v[k], b = v[k + 16];
+            v[k] = fadd2(a, b);
+            v[k + 16] = mul_w32(fsub2(a, b), k);
+        }
+    }
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+#pragma unroll
+        for (int g = 0; g < 32; g += 2 * half) {
+#pragma unroll
+            for (int k = 0; k < half; ++k) {
+                const float2 a = v[g + k], b = v[g + k + half];
+                v[g + k] = fadd2(a, b);
+                v[g + k + half] = mul_w32(fsub2(a, b), k * (16 / half));
+            }
+        }
+    }
+}
+
+// named barriers (0 is __syncthreads): spectrum buffer s is FULL / EMPTY
+constexpr int kBarFull = 1, kBarEmpty = 3;
+__device__ __forceinline__ void bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void stg256(float* dst, const float (&o)[8]) {  // one 32-byte sector per lane (STG.256)
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
+                 "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                 : "memory");
+}
+
+constexpr int kHB = 8;            // hops per batch = FFT warps per CTA
+constexpr int kFftThreads = 32 * kHB;
+constexpr int kIntThreads = 256;  // interpolation threads per CTA, each owns up to KC channels for the whole launch
+constexpr int kThreads = kFftThreads + kIntThreads;
+constexpr int kAnchorEvery = 16;  // batches between re-reads of the exact phase table (the recurrence runs in between)
+constexpr size_t kSpecBytes = (size_t)2 * kHB * kHopStride * 8;  // double-buffered spectra
+
+// Persistent, warp-specialised: CTA j owns a contiguous run of batches (kHB hops each). Warps 0..7 (producers) each
+// compute the 1024-point spectrum of one hop of the batch into spectrum buffer s = batch & 1; warps 8..15
+// (consumers) read every channel's frequency off those spectra while the producers are already transforming the
+// next batch. Hand-over by named barriers (bar.arrive / bar.sync), no __syncthreads in the loop.
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+    demod_chan_kernel(DemodLaunch p, ChanLaunch c, uint32_t n_batches, uint32_t batches_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* spec = reinterpret_cast<float2*>(smem);
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t s0 = blockIdx.x * batches_per_cta;
+    const uint32_t s1 = min(n_batches, s0 + batches_per_cta);
+    if (s0 >= s1) return;
+
+    if (warp < (uint32_t)kHB) {
+        // ================= producers: hop h = warp of every batch =================
+        // window of hop b = IQ blocks b-31 .. b; element j = 32 j1 + lane sits in block b-31 + 2 j1 + (lane >> 4)
+        long long blk = (long long)p.b0 + (long long)s0 * kHB + (long long)warp - 31 + (long long)(lane >> 4);
+        uint32_t row;
+        {
+            long long m = ((long long)p.ring_off + blk) % (long long)p.ring_blocks;
+            if (m < 0) m += p.ring_blocks;
+            row = (uint32_t)m;
+        }
+        float wv[16];  // this lane's 16 window taps (constant over the launch)
+#pragma unroll
+        for (int j1 = 0; j1 < 16; ++j1) wv[j1] = __ldg(c.window + 32 * j1 + lane);
+        for (uint32_t i = s0; i < s1; ++i) {
+            const uint32_t s = (i - s0) & 1u;
+            if (i - s0 >= 2) bar_sync(kBarEmpty + s, kThreads);  // consumers are done with this buffer
+            float2* buf = spec + (size_t)(s * kHB + warp) * kHopStride;
+            float2 v[32];
+            // pass 1: lane = j2, 32-point DFT over j1 of u[32 j1 + j2], u = x * window (j1 >= 16 is the zero padding)
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) {
+                uint32_t r = row + 2 * j1;  // < 2 * ring_blocks
+                if (r >= p.ring_blocks) r -= p.ring_blocks;
+                float2 x = make_float2(0.0f, 0.0f);
+                if (blk + 2 * j1 >= 0) x = __ldg(p.iq_ring + (size_t)r * 16 + (lane & 15u));  // zero history before the slot
+                v[j1] = fmul2(x, bc(wv[j1]));
+            }
+            fft32<true>(v);
+            // twiddle W1024^(j2 q1) * i^q1 and transpose through the hop buffer (rows of 33: conflict-free both ways)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int q1 = bitrev5(k);
+                const float2 w = __ldg(c.twiddle + 32 * q1 + lane);
+                const float2 a = v[k];
+                buf[q1 * 33 + lane] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+            }
+            __syncwarp();
+            // pass 2: lane = q1, 32-point DFT over j2 -> bins q1 + 32 q2
+#pragma unroll
+            for (int j2 = 0; j2 < 32; ++j2) v[j2] = buf[lane * 33 + j2];
+            __syncwarp();
+            fft32<false>(v);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) buf[32 * bitrev5(k) + lane] = v[k];
+            if (lane < 8) buf[kN + lane] = v[0];  // bins 0..7 again behind bin 1023: stencils never wrap
+            bar_arrive(kBarFull + s, kThreads);
+            blk += kHB;
+            row += kHB;
+            if (row >= p.ring_blocks) row -= p.ring_blocks;
+        }
+    } else {
+        // ================= consumers: thread owns channels tid, tid+256, ... =================
+        const uint32_t tid = t - kFftThreads;
+        uint32_t off[KC];      // byte offset of the channel's first stencil bin inside a hop buffer
+        float wg[KC][8];       // interpolation weights
+        float2 rot[KC], pinc[KC], R[KC];
+        float sgn[KC], mx[KC];
+        bool have[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const uint32_t ch = tid + k * kIntThreads;
+            have[k] = ch < p.n_channels;
+            const float4* kc = reinterpret_cast<const float4*>(c.consts + (have[k] ? ch : 0));
+            const float4 k0 = __ldg(kc), k1 = __ldg(kc + 1), k2 = __ldg(kc + 2), k3 = __ldg(kc + 3);
+            off[k] = ((uint32_t)__float_as_int(k0.x) & (uint32_t)(kN - 1)) * 8u;
+            sgn[k] = k0.y;
+            rot[k] = make_float2(k0.z, k0.w);
+            wg[k][0] = k1.x, wg[k][1] = k1.y, wg[k][2] = k1.z, wg[k][3] = k1.w;
+            wg[k][4] = k2.x, wg[k][5] = k2.y, wg[k][6] = k2.z, wg[k][7] = k2.w;
+            pinc[k] = make_float2(k3.x, k3.y);
+            R[k] = make_float2(0.0f, 0.0f);
+            mx[k] = 0.0f;
+        }
+        const unsigned char* spec_b = smem;
+        for (uint32_t i = s0; i < s1; ++i) {
+            const uint32_t s = (i - s0) & 1u;
+            const uint32_t bb = p.b0 + i * kHB;
+            const bool anchor = ((i - s0) % kAnchorEvery) == 0;
+            if (anchor) {
+                // R = P_c[bb] * rot_c from the exact table; between anchors R *= phase_inc per hop
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    if (!have[k]) continue;
+                    const float2 P = __ldg(p.phase[tid + k * kIntThreads] + bb);
+                    R[k] = make_float2(P.x * rot[k].x - P.y * rot[k].y, P.x * rot[k].y + P.y * rot[k].x);
+                }
+            }
+            bar_sync(kBarFull + s, kThreads);
+            const bool full = bb + kHB <= p.b1 && (bb & 7u) == 0;  // whole batch, 32-byte aligned row segment
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (!have[k]) continue;
+                const unsigned char* base = spec_b + (size_t)s * kHB * kHopStride * 8 + off[k];
+                float out[kHB];
+#pragma unroll
+                for (int h = 0; h < kHB; ++h) {
+                    const float4* bins = reinterpret_cast<const float4*>(base + (size_t)h * kHopStride * 8);
+                    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 two = bins[q];
+                        acc = ffma2(make_float2(two.x, two.y), bc(wg[k][2 * q]), acc);
+                        acc = ffma2(make_float2(two.z, two.w), bc(wg[k][2 * q + 1]), acc);
+                    }
+                    const float2 r = R[k];
+                    // audio[b] = {+Re, -Im*sign, -Re, +Im*sign}[b & 3] of acc*R; bb is a multiple of 4
+                    float o;
+                    if ((h & 3) == 0) o = acc.x * r.x - acc.y * r.y;
+                    else if ((h & 3) == 1) o = -(acc.x * r.y + acc.y * r.x) * sgn[k];
+                    else if ((h & 3) == 2) o = -(acc.x * r.x - acc.y * r.y);
+                    else o = (acc.x * r.y + acc.y * r.x) * sgn[k];
+                    out[h] = o;
+                    R[k] = make_float2(r.x * pinc[k].x - r.y * pinc[k].y, r.x * pinc[k].y + r.y * pinc[k].x);
+                }
+                float* dst = p.audio + (size_t)(tid + k * kIntThreads) * p.af_stride + bb;
+                if (full) {
+                    stg256(dst, out);
+                    float m = mx[k];
+#pragma unroll
+                    for (int h = 0; h < kHB; ++h) m = fmaxf(m, fabsf(out[h]));
+                    mx[k] = m;
+                } else {
+#pragma unroll
+                    for (int h4 = 0; h4 < kHB; h4 += 4) {
+                        if (bb + h4 < p.b1) {  // b1 is a multiple of 4
+                            *reinterpret_cast<float4*>(dst + h4) = make_float4(out[h4], out[h4 + 1], out[h4 + 2], out[h4 + 3]);
+                            mx[k] = fmaxf(mx[k], fmaxf(fmaxf(fabsf(out[h4]), fabsf(out[h4 + 1])), fmaxf(fabsf(out[h4 + 2]), fabsf(out[h4 + 3]))));
+                        }
+                    }
+                }
+            }
+            if (i + 2 < s1) bar_arrive(kBarEmpty + s, kThreads);  // (nobody waits for the last two)
+        }
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (!have[k]) continue;
+            const unsigned bits = __float_as_uint(mx[k]);
+            unsigned* dst = p.maxbits + tid + k * kIntThreads;
+            if (bits != 0 && bits > __ldcg(dst)) atomicMax(dst, bits);
+        }
+    }
+}
+
+std::mutex g_attr_mu;
+std::set<std::pair<int, const void*>> g_attr_done;
+
+cudaError_t prepare(const void* kern, int* sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    if (g_attr_done.count({dev, kern})) return cudaSuccess;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
+    g_attr_done.insert({dev, kern});
+    return cudaSuccess;
+}
+
+template <int KC>
+cudaError_t launch_t(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
+    auto kern = demod_chan_kernel<KC>;
+    int sms = 0;
+    cudaError_t e = prepare(reinterpret_cast<const void*>(kern), &sms);
+    if (e != cudaSuccess) return e;
+    const uint32_t n_batches = (p.b1 - p.b0 + kHB - 1) / kHB;
+    // one CTA per SM, contiguous runs of batches (anchored phase recurrence, sequential IQ reads)
+    const uint32_t per_cta = (n_batches + (uint32_t)sms - 1) / (uint32_t)sms;
+    const uint32_t grid = (n_batches + per_cta - 1) / per_cta;
+    kern<<<grid, kThreads, kSpecBytes, s>>>(p, c, n_batches, per_cta);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+uint32_t chan_max_channels() { return kChanMaxChannels; }
+
+cudaError_t launch_demod_chan(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
+    if (p.block_size != 16 || c.taps != kChanTaps || p.n_channels == 0 || p.n_channels > kChanMaxChannels ||
+        p.ring_blocks < 64 || (p.b0 & 3u) || (p.b1 & 3u) || (p.af_stride & 7u))
+        return cudaErrorInvalidValue;
+    if (p.b1 <= p.b0) return cudaSuccess;
+    switch ((p.n_channels + kIntThreads - 1) / kIntThreads) {
+        case 1: return launch_t<1>(p, c, s);
+        case 2: return launch_t<2>(p, c, s);
+        case 3: return launch_t<3>(p, c, s);
+        default: return launch_t<4>(p, c, s);
+    }
+}
+
+}  // namespace cwsl

@@ -41,6 +41,25 @@ struct QuantLaunch {
     float* max_out = nullptr;      // [n_channels] maxVal of prepareAudio
 };
 
+// Extra inputs of the STFT channelizer kernel (cwsl_chan.cu); tables from cwsl_tables.hpp chan_*.
+constexpr int kChanTaps = 8;                   // stencil bins per channel: Kaiser-Bessel kernel of width 7 on an even-aligned stencil
+constexpr int kChanKernelWidth = 7;
+constexpr uint32_t kChanMaxChannels = 1024;    // per launch (each interpolation thread keeps <= 4 channels in registers)
+struct alignas(16) ChanConst {   // per-channel constants, four 16-byte loads
+    int q0;           // first grid bin of the interpolation stencil, even (bins are taken mod 1024)
+    float sign;       // +1 USB / -1 LSB
+    float rot[2];     // e^{-i 240 w_c}
+    float wgt[kChanTaps];  // real interpolation weights of bins q0 .. q0+7
+    float pinc[2];    // the reference's float phase_inc (per-hop NCO step between phase-table anchors)
+    float pad[2];
+};
+struct ChanLaunch {
+    const float* window = nullptr;    // [512]  taps / psihat((j-256)/1024)
+    const float2* twiddle = nullptr;  // [32][32] W1024^(j2*q1) * i^q1 at [q1*32 + j2]
+    const ChanConst* consts = nullptr;  // [n_channels]
+    int taps = kChanTaps;
+};
+
 // Upload the normalised low-pass taps for one block size into constant memory.
 cudaError_t upload_taps(uint32_t block_size, const float* taps /*[32*block_size]*/);
 // The compile-time taps the fast kernel uses as immediates, transposed [m*32+n]; nullptr if unsupported.
@@ -53,6 +72,8 @@ cudaError_t launch_phase_tables(const float2* phase_inc /*[n]*/, float2* const* 
 cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s);         // tiled, production
 cudaError_t launch_demod_exact_gather(const DemodLaunch& p, cudaStream_t s);  // one thread per output, cross-check
 cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s);
+// STFT channelizer (192 kHz receivers, <= kChanMaxChannels channels per launch)
+cudaError_t launch_demod_chan(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s);
 cudaError_t launch_quantise(const QuantLaunch& p, cudaStream_t s);
 cudaError_t launch_clear_u32(unsigned* p, uint32_t n, cudaStream_t s);
 

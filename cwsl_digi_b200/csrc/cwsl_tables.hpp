@@ -70,6 +70,7 @@ struct NcoTables {
     std::vector<std::complex<float>> tone;  // [block_size]
     std::complex<float> phase_inc;
     float sign = 1.0f;
+    float phase_delta = 0.0f;               // radians per input sample, source/SSBD.hpp:111
 };
 
 // false where SSBD::Tune throws (source/SSBD.hpp:100-103)
@@ -81,11 +82,85 @@ inline bool nco_tables(const SsbdGeometry& g, int32_t demod_freq_hz, bool is_usb
     const float sign = static_cast<float>(is_usb ? 1.0 : -1.0);
     const float phase_delta = static_cast<float>(-2.0 * kPi * (F + sign * B / 2.0) / static_cast<double>(Fs));
     t->sign = sign;
+    t->phase_delta = phase_delta;
     t->tone.resize(g.block_size);
     for (size_t n = 0; n < g.block_size; ++n)
         t->tone[n] = std::exp(std::complex<float>(0.0, phase_delta * n));
     t->phase_inc = std::exp(std::complex<float>(0.0, phase_delta * g.block_size));
     return true;
+}
+
+// ---- STFT channelizer tables (cwsl_chan.cu). Not reference arithmetic: a type-2 non-uniform FFT of the
+// reference's window (512 taps on a 1024-point grid) with a Kaiser-Bessel interpolation kernel, all in double.
+constexpr uint32_t kChanGrid = 1024;
+
+struct ChanKernel {
+    int w;
+    double beta, i0beta;
+    explicit ChanKernel(int taps) : w(taps) {
+        const double sigma = 2.0;  // grid / window length
+        beta = kPi * std::sqrt((w / sigma) * (w / sigma) * (sigma - 0.5) * (sigma - 0.5) - 0.8);
+        i0beta = std::cyl_bessel_i(0.0, beta);
+    }
+    double psi(double t) const {  // interpolation kernel, support |t| <= w/2 bins
+        const double a = 1.0 - (2.0 * t / w) * (2.0 * t / w);
+        return a < 0.0 ? 0.0 : std::cyl_bessel_i(0.0, beta * std::sqrt(a)) / i0beta;
+    }
+    double psihat(double s) const {  // its Fourier transform at s cycles per bin (|pi w s| < beta here)
+        const double z2 = beta * beta - (kPi * w * s) * (kPi * w * s);
+        const double z = std::sqrt(z2);
+        return w * std::sinh(z) / z / i0beta;
+    }
+};
+
+// window[j] = h[j] / psihat((j - 256)/1024): the low-pass taps pre-compensated for the interpolation kernel
+inline std::vector<float> chan_window(const SsbdGeometry& g, int width) {
+    const std::vector<float> h = lowpass_taps(g);
+    const ChanKernel k(width);
+    std::vector<float> w(h.size());
+    for (size_t j = 0; j < h.size(); ++j)
+        w[j] = static_cast<float>((double)h[j] / k.psihat(((double)j - h.size() / 2.0) / kChanGrid));
+    return w;
+}
+
+// twiddle[q1*32 + j2] = W1024^(j2*q1) * i^q1 (inter-pass twiddle of the 32x32 FFT and the rotation that moves
+// the phase reference of the spectrum to the window centre)
+inline std::vector<std::complex<float>> chan_twiddles() {
+    std::vector<std::complex<float>> t(32 * 32);
+    for (int q1 = 0; q1 < 32; ++q1)
+        for (int j2 = 0; j2 < 32; ++j2) {
+            const double a = -2.0 * kPi * ((j2 * q1) % (int)kChanGrid) / kChanGrid + kPi / 2.0 * (q1 & 3);
+            t[q1 * 32 + j2] = std::complex<float>((float)std::cos(a), (float)std::sin(a));
+        }
+    return t;
+}
+
+struct ChanChannel {
+    int q0 = 0;                  // first bin of the stencil (may be negative: bins are taken mod 1024)
+    std::vector<float> wgt;      // [taps]
+    std::complex<float> rot;     // e^{-i 240 w}
+};
+
+// Per-channel constants: the channel's effective NCO frequency is the per-block angle of the reference's own
+// float phase_inc (unwrapped with phase_delta) divided by the block size.
+// The stencil is `taps` bins starting at an even bin and covers the support of the width-`width` kernel
+// (taps >= width + 1), so the kernel can read it as aligned bin pairs.
+inline ChanChannel chan_channel(const SsbdGeometry& g, const NcoTables& t, int width, int taps) {
+    const ChanKernel k(width);
+    double theta = std::atan2((double)t.phase_inc.imag(), (double)t.phase_inc.real());
+    const double nominal = (double)t.phase_delta * g.block_size;
+    theta += 2.0 * kPi * std::round((nominal - theta) / (2.0 * kPi));
+    const double omega = theta / g.block_size;
+    double nu = std::fmod(-omega * kChanGrid / (2.0 * kPi), (double)kChanGrid);
+    if (nu < 0) nu += kChanGrid;
+    ChanChannel c;
+    c.q0 = (int)std::ceil(nu - width / 2.0);
+    if (c.q0 & 1) c.q0 -= 1;
+    c.wgt.resize(taps);
+    for (int i = 0; i < taps; ++i) c.wgt[i] = (float)k.psi(nu - (c.q0 + i));
+    const double a = -omega * (double)(g.filt_order - g.block_size - g.filt_order / 2);
+    c.rot = std::complex<float>((float)std::cos(a), (float)std::sin(a));
+    return c;
 }
 
 inline size_t af_size(double period_s) {  // source/Instance.cpp:149

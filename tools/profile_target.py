@@ -10,7 +10,7 @@ from cwsl_digi_b200 import synth
 
 C_ = int(os.environ.get("PROF_CHANNELS", "1024"))
 N_ = int(os.environ.get("PROF_SLOTS", "3"))
-MODE = cw.MODE_EXACT if os.environ.get("PROF_MODE", "fast") == "exact" else cw.MODE_FAST
+MODE = {"exact": cw.MODE_EXACT, "fast": cw.MODE_FAST, "stft": cw.MODE_STFT}[os.environ.get("PROF_MODE", "fast")]
 FS, IQ_LEN = 192000, 2048
 nblk = 15 * FS // IQ_LEN
 x = (torch.randn(nblk * IQ_LEN * 2, device="cuda") * 300).contiguous()
