@@ -53,7 +53,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--receivers", type=int, default=N_RECEIVERS, help="total receivers over all ranks")
     ap.add_argument("--channels", type=int, default=N_CHANNELS)
-    ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--mode", default="stft", choices=["stft", "fast", "exact"],
+                    help="stft: FFT channelizer kernel (<= 1 LSB, default); fast: direct-form FFMA2 kernel (<= 1 LSB); "
+                         "exact: bit-identical to the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-station", action="store_true")
@@ -219,7 +221,7 @@ def run_b200(a):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    mode = cw.MODE_FAST if a.mode == "fast" else cw.MODE_EXACT
+    mode = {"stft": cw.MODE_STFT, "fast": cw.MODE_FAST, "exact": cw.MODE_EXACT}[a.mode]
     from cwsl_digi_b200.sharding import receivers_of_rank
     my_rx = receivers_of_rank(a.receivers, rank, world)     # one receiver/band per GPU, round-robin
     n_blocks = int(PERIOD * FS) // IQ_LEN                   # 1406 IQ blocks = 2 879 488 samples
@@ -399,34 +401,62 @@ def run_b200(a):
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "demod_fast_traffic.json")))["dram_bytes_per_launch"]
         except Exception:  # noqa: BLE001
             pass
-        roofline = dict(bound="fp32_fma_pipe", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
-                        frac=achieved_tf / peak_tf, traffic=traffic,
-                        kernel="demod_fast_kernel<16,4,128,2>" if a.mode == "fast" else "demod_exact_tiled_kernel<16,128,3,24>",
-                        launch_ms=launch_ms, launches_timed=demod_launches,
-                        kernel_share_of_step=demod_ms / (ms_total if ms_total > 0 else 1),
-                        share_note="demod launch time / timed region, CUDA events. The normalise+quantise pass of "
-                                   "receiver r (3.6 % of the kernel time when serialised, profiles/r1_launches_v3.csv) "
-                                   "runs on the receiver's post stream and overlaps the demodulation of receiver r+1, "
-                                   "so the demod kernel covers ~100 % of the region",
-                        peak_source="register-resident FMA microbenchmark with immediate operands run in this process "
-                                    "(cwsl_measure_fp32_peak, max of the FFMA2 and FFMA forms); MEASURED_PEAKS.json has "
-                                    "no FP32-pipe figure. Nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; "
-                                    f"measured FFMA2 {fp32['ffma2_tflops']:.1f}, scalar FFMA {fp32['ffma_tflops']:.1f}",
-                        algorithmic="134 flop per channel-sample (SURVEY.md 8d) x channels x IQ samples per launch; "
-                                    "frac can exceed 1: the kernel folds the symmetric taps and executes fewer "
-                                    "multiplies than the direct form the 134 counts (see 'executed')",
-                        executed=(dict(pipe_instr_per_block=FAST_PIPE_INSTR_PER_BLOCK,
-                                       flop_slots_per_ch_sample=FAST_PIPE_INSTR_PER_BLOCK * 4 / 16 * FAST_TILE_OVERHEAD,
-                                       tflops=FAST_PIPE_INSTR_PER_BLOCK * 4 / 16 * FAST_TILE_OVERHEAD * a.channels * n_iq
-                                       / (launch_ms * 1e-3) / 1e12,
-                                       frac_of_peak=FAST_PIPE_INSTR_PER_BLOCK * 4 / 16 * FAST_TILE_OVERHEAD * a.channels
-                                       * n_iq / (launch_ms * 1e-3) / 1e12 / peak_tf,
-                                       note="FMA-pipe lane-slots actually issued (packed f32x2 instr x 2 lanes x 2), "
-                                            "tile overlap included = FMA-pipe utilisation")
-                                  if a.mode == "fast" else None),
-                        hbm=dict(achieved_gbs=bytes_per_launch / (launch_ms * 1e-3) / 1e9, peak_gbs=hbm_peak,
-                                 frac=bytes_per_launch / (launch_ms * 1e-3) / 1e9 / hbm_peak,
-                                 bytes_per_launch=bytes_per_launch, peak_source="MEASURED_PEAKS.json hbm_gbs"))
+        if a.mode == "stft":
+            # The channelizer does ~1.5 FMA-pipe instructions per channel-sample instead of the direct form's 24, so
+            # the path is byte-bound: algorithmic HBM bytes of one launch = the receiver's IQ read once + the float
+            # audio written once (8 B/C + 4 B/16 per channel-sample; the phase table is only read at
+            # anchors). The kernel's own limiter is shared-memory bandwidth (ncu: 62 % of the LSU wavefront peak,
+            # FMA pipe 40 %, DRAM 15 %), see profiles/r1_demod_chan_ncu_full.csv.
+            stft_bytes = n_iq * 8 + a.channels * (n_iq // 16) * 4
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "demod_chan_traffic.json")))["dram_bytes_per_launch"]
+            except Exception:  # noqa: BLE001
+                traffic = None
+            gbs = stft_bytes / (launch_ms * 1e-3) / 1e9
+            roofline = dict(bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak, traffic=traffic,
+                            kernel="demod_chan_kernel<4> (STFT channelizer: 8 FFT warps + 8 interpolation warps per SM)",
+                            launch_ms=launch_ms, launches_timed=demod_launches,
+                            kernel_share_of_step=demod_ms / (ms_total if ms_total > 0 else 1),
+                            share_note="demod launch time / timed region, CUDA events; the quantise pass of receiver r "
+                                       "(HBM-bound, ~0.2 ms) runs on the post stream beside the demodulation of r+1",
+                            peak_source="MEASURED_PEAKS.json hbm_gbs (sustained)",
+                            algorithmic=f"{stft_bytes} B per launch = IQ {n_iq * 8} B read once + float audio "
+                                        f"{a.channels * (n_iq // 16) * 4} B written once",
+                            limiter="shared-memory bandwidth (per hop: 1024 channels x 8 bins x 8 B of spectrum reads + "
+                                    "the FFT transposes), not HBM: ncu l1tex shared wavefronts 62 % of peak, FMA pipe 40 %",
+                            direct_form_equivalent=dict(
+                                tflops=achieved_tf, fp32_peak_tflops=peak_tf,
+                                note="134 flop per channel-sample (SURVEY.md 8d, direct form) x throughput, for "
+                                     "comparison with the fast/exact modes only: the channelizer does not execute them"))
+        else:
+            roofline = dict(bound="fp32_fma_pipe", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
+                            frac=achieved_tf / peak_tf, traffic=traffic,
+                            kernel="demod_fast_kernel<16,4,128,2>" if a.mode == "fast" else "demod_exact_tiled_kernel<16,128,3,24>",
+                            launch_ms=launch_ms, launches_timed=demod_launches,
+                            kernel_share_of_step=demod_ms / (ms_total if ms_total > 0 else 1),
+                            share_note="demod launch time / timed region, CUDA events. The normalise+quantise pass of "
+                                       "receiver r (3.6 % of the kernel time when serialised, profiles/r1_launches_v3.csv) "
+                                       "runs on the receiver's post stream and overlaps the demodulation of receiver r+1, "
+                                       "so the demod kernel covers ~100 % of the region",
+                            peak_source="register-resident FMA microbenchmark with immediate operands run in this process "
+                                        "(cwsl_measure_fp32_peak, max of the FFMA2 and FFMA forms); MEASURED_PEAKS.json has "
+                                        "no FP32-pipe figure. Nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; "
+                                        f"measured FFMA2 {fp32['ffma2_tflops']:.1f}, scalar FFMA {fp32['ffma_tflops']:.1f}",
+                            algorithmic="134 flop per channel-sample (SURVEY.md 8d) x channels x IQ samples per launch; "
+                                        "frac can exceed 1: the kernel folds the symmetric taps and executes fewer "
+                                        "multiplies than the direct form the 134 counts (see 'executed')",
+                            executed=(dict(pipe_instr_per_block=FAST_PIPE_INSTR_PER_BLOCK,
+                                           flop_slots_per_ch_sample=FAST_PIPE_INSTR_PER_BLOCK * 4 / 16 * FAST_TILE_OVERHEAD,
+                                           tflops=FAST_PIPE_INSTR_PER_BLOCK * 4 / 16 * FAST_TILE_OVERHEAD * a.channels * n_iq
+                                           / (launch_ms * 1e-3) / 1e12,
+                                           frac_of_peak=FAST_PIPE_INSTR_PER_BLOCK * 4 / 16 * FAST_TILE_OVERHEAD * a.channels
+                                           * n_iq / (launch_ms * 1e-3) / 1e12 / peak_tf,
+                                           note="FMA-pipe lane-slots actually issued (packed f32x2 instr x 2 lanes x 2), "
+                                                "tile overlap included = FMA-pipe utilisation")
+                                      if a.mode == "fast" else None),
+                            hbm=dict(achieved_gbs=bytes_per_launch / (launch_ms * 1e-3) / 1e9, peak_gbs=hbm_peak,
+                                     frac=bytes_per_launch / (launch_ms * 1e-3) / 1e9 / hbm_peak,
+                                     bytes_per_launch=bytes_per_launch, peak_source="MEASURED_PEAKS.json hbm_gbs"))
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
@@ -527,7 +557,7 @@ def run_station(cw, torch, dist, rank, world, local, mode, n_receivers=8, hyper_
                          "streamed from pinned host memory in 1.5 s pushes through a 3 s device ring, slot edges per mode, "
                          "int16 audio of every slot copied back to the host",
                 x_realtime=hyper_s / wall, wall_s=wall, value=chs / wall / 1e6, unit=UNIT,
-                receivers_per_rank=len(mine), slots_finished_per_rank=slots, mode="fast" if mode == 1 else "exact")
+                receivers_per_rank=len(mine), slots_finished_per_rank=slots, mode={0: "exact", 1: "fast", 2: "stft (7-channel groups: FAST kernel)"}[mode])
 
 
 def main():

@@ -128,7 +128,9 @@ constexpr size_t kSpecBytes = (size_t)2 * kHB * kHopStride * 8;  // double-buffe
 // (consumers) read every channel's frequency off those spectra while the producers are already transforming the
 // next batch. Hand-over by named barriers (bar.arrive / bar.sync), no __syncthreads in the loop.
 template <int KC>
-__global__ void __launch_bounds__(kThreads, 1)
+// 104 registers x 512 threads leave room on every SM for one CTA of the (HBM-bound) quantise kernel of the previous
+// receiver, which then runs underneath this (shared-memory-bound) kernel instead of after it.
+__global__ void __maxnreg__(104)
     demod_chan_kernel(DemodLaunch p, ChanLaunch c, uint32_t n_batches, uint32_t batches_per_cta) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* spec = reinterpret_cast<float2*>(smem);

@@ -730,7 +730,11 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s) {
 // Each operation is a separately rounded float op, as compiled from the reference with strict
 // IEEE flags. Samples past write_index are the zero tail: (int16)(0*factor + 0.5f) = 0.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) quantise_kernel(QuantLaunch p) {
+// Each thread converts kQuantVec groups of 8 samples, all of its loads issued before the first conversion: the pass
+// is pure HBM traffic, and it usually runs in the one CTA slot per SM that the STFT demodulator of the NEXT receiver
+// leaves free, so bytes in flight per thread are what make it fast.
+constexpr int kQuantThreads = 128, kQuantVec = 4;
+__global__ void __launch_bounds__(kQuantThreads) quantise_kernel(QuantLaunch p) {
     const uint32_t c = blockIdx.y;
     const float maxv = __uint_as_float(p.maxbits[c]);
     float factor = __fdiv_rn(32767.0f, __fadd_rn(maxv, 1.0f));
@@ -739,44 +743,56 @@ __global__ void __launch_bounds__(256) quantise_kernel(QuantLaunch p) {
         if (p.factor_out) p.factor_out[c] = factor;
         if (p.max_out) p.max_out[c] = maxv;
     }
-    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8u;
-    if (i0 >= p.af_size) return;
     const float* __restrict__ src = p.audio + (size_t)c * p.af_stride;
     int16_t* __restrict__ dst = p.out + (size_t)c * p.af_size;
     const bool vec = (p.af_size % 8u == 0) && (p.af_stride % 4u == 0);
-    short q[8];
-    if (vec && i0 + 8 <= p.write_index) {
-        const float4 a = *reinterpret_cast<const float4*>(src + i0);
-        const float4 b = *reinterpret_cast<const float4*>(src + i0 + 4);
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t base = blockIdx.x * (kQuantThreads * 8u * kQuantVec) + threadIdx.x * 8u;
+    float4 a[kQuantVec], b[kQuantVec];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) q[e] = (short)__float2int_rz(__fadd_rn(__fmul_rn(v[e], factor), 0.5f));
-    } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const uint32_t i = i0 + e;
-            const float v = (i < p.write_index) ? src[i] : 0.0f;
-            q[e] = (short)__float2int_rz(__fadd_rn(__fmul_rn(v, factor), 0.5f));
+    for (int v = 0; v < kQuantVec; ++v) {
+        const uint32_t i0 = base + v * (kQuantThreads * 8u);
+        if (vec && i0 + 8 <= p.write_index) {
+            a[v] = __ldcs(reinterpret_cast<const float4*>(src + i0));      // streaming: read exactly once
+            b[v] = __ldcs(reinterpret_cast<const float4*>(src + i0 + 4));
         }
     }
-    if (vec) {
-        int4 pk;
-        pk.x = (int)((unsigned short)q[0] | ((unsigned)(unsigned short)q[1] << 16));
-        pk.y = (int)((unsigned short)q[2] | ((unsigned)(unsigned short)q[3] << 16));
-        pk.z = (int)((unsigned short)q[4] | ((unsigned)(unsigned short)q[5] << 16));
-        pk.w = (int)((unsigned short)q[6] | ((unsigned)(unsigned short)q[7] << 16));
-        *reinterpret_cast<int4*>(dst + i0) = pk;
-    } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if (i0 + e < p.af_size) dst[i0 + e] = q[e];
+    for (int v = 0; v < kQuantVec; ++v) {
+        const uint32_t i0 = base + v * (kQuantThreads * 8u);
+        if (i0 >= p.af_size) continue;
+        short q[8];
+        if (vec && i0 + 8 <= p.write_index) {
+            const float x[8] = {a[v].x, a[v].y, a[v].z, a[v].w, b[v].x, b[v].y, b[v].z, b[v].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) q[e] = (short)__float2int_rz(__fadd_rn(__fmul_rn(x[e], factor), 0.5f));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t i = i0 + e;
+                const float x = (i < p.write_index) ? src[i] : 0.0f;
+                q[e] = (short)__float2int_rz(__fadd_rn(__fmul_rn(x, factor), 0.5f));
+            }
+        }
+        if (vec) {
+            int4 pk;
+            pk.x = (int)((unsigned short)q[0] | ((unsigned)(unsigned short)q[1] << 16));
+            pk.y = (int)((unsigned short)q[2] | ((unsigned)(unsigned short)q[3] << 16));
+            pk.z = (int)((unsigned short)q[4] | ((unsigned)(unsigned short)q[5] << 16));
+            pk.w = (int)((unsigned short)q[6] | ((unsigned)(unsigned short)q[7] << 16));
+            __stcs(reinterpret_cast<int4*>(dst + i0), pk);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (i0 + e < p.af_size) dst[i0 + e] = q[e];
+        }
     }
 }
 
 cudaError_t launch_quantise(const QuantLaunch& p, cudaStream_t s) {
     if (p.n_channels == 0 || p.af_size == 0) return cudaSuccess;
-    dim3 grid((p.af_size + 2047) / 2048, p.n_channels);
-    quantise_kernel<<<grid, 256, 0, s>>>(p);
+    const uint32_t per_cta = kQuantThreads * 8u * kQuantVec;
+    dim3 grid((p.af_size + per_cta - 1) / per_cta, p.n_channels);
+    quantise_kernel<<<grid, kQuantThreads, 0, s>>>(p);
     return cudaGetLastError();
 }
 
