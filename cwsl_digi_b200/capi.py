@@ -13,7 +13,7 @@ MODE_EXACT, MODE_FAST, MODE_STFT = 0, 1, 2
 # every symbol include/cwsl_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "cwsl_abi_version", "cwsl_last_error", "cwsl_device_count", "cwsl_ssbd_params", "cwsl_build_tables",
-    "cwsl_af_size", "cwsl_accepted_blocks", "cwsl_rx_create", "cwsl_rx_destroy", "cwsl_rx_set_mode",
+    "cwsl_stft_tables", "cwsl_stft_channel", "cwsl_af_size", "cwsl_accepted_blocks", "cwsl_rx_create", "cwsl_rx_destroy", "cwsl_rx_set_mode",
     "cwsl_rx_add_group", "cwsl_rx_add_channel", "cwsl_rx_num_groups", "cwsl_rx_num_channels",
     "cwsl_rx_group_af_size", "cwsl_rx_push_iq", "cwsl_rx_push_iq_device", "cwsl_rx_bind_device_iq",
     "cwsl_rx_process", "cwsl_rx_end_slot", "cwsl_rx_device_audio", "cwsl_rx_copy_device_audio", "cwsl_rx_read_float_audio",
@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
     L.cwsl_device_count.restype = C.c_int
     L.cwsl_ssbd_params.argtypes = [u32, C.POINTER(u32)]
     L.cwsl_build_tables.argtypes = [u32, i32, C.c_int, vp, vp, vp]
+    L.cwsl_stft_tables.argtypes = [u32, vp, vp]
+    L.cwsl_stft_channel.argtypes = [u32, i32, C.c_int, C.POINTER(C.c_int32), vp, vp]
     L.cwsl_af_size.restype = sz
     L.cwsl_af_size.argtypes = [C.c_double]
     L.cwsl_accepted_blocks.restype = sz
@@ -133,6 +135,23 @@ def build_tables(fs: int, demod_freq: int, is_usb: bool = True) -> dict:
     pinc = np.zeros(2, np.float32)
     _check(lib().cwsl_build_tables(fs, demod_freq, int(is_usb), filt.ctypes.data, tone.ctypes.data, pinc.ctypes.data))
     return dict(filter=filt, tone=tone, phase_inc=pinc)
+
+
+def stft_tables(fs: int = 192000) -> dict:
+    """Host-side shared tables of CWSL_MODE_STFT: deconvolved window [512], FFT twiddles complex64 [32, 32]."""
+    w = np.zeros(512, np.float32)
+    tw = np.zeros(2 * 1024, np.float32)
+    _check(lib().cwsl_stft_tables(fs, w.ctypes.data, tw.ctypes.data))
+    return dict(window=w, twiddle=tw.view(np.complex64).reshape(32, 32))
+
+
+def stft_channel(fs: int, demod_freq: int, is_usb: bool = True) -> dict:
+    """Per-channel constants of CWSL_MODE_STFT: first stencil bin, 8 weights, rotation e^{-i 240 w}."""
+    q0 = C.c_int32()
+    wgt = np.zeros(8, np.float32)
+    rot = np.zeros(2, np.float32)
+    _check(lib().cwsl_stft_channel(fs, demod_freq, int(is_usb), C.byref(q0), wgt.ctypes.data, rot.ctypes.data))
+    return dict(q0=q0.value, wgt=wgt, rot=complex(rot[0], rot[1]))
 
 
 def measure_fp32_peak(device: int = 0) -> dict:

@@ -555,6 +555,40 @@ int cwsl_build_tables(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, f
     return CWSL_OK;
 }
 
+int cwsl_stft_tables(uint32_t sample_rate, float* window, float* twiddle) {
+    cwsl::SsbdGeometry g;
+    if (!cwsl::ssbd_geometry(sample_rate, &g)) return fail(CWSL_ERR_INVALID, "Fs/B must be an even integer >= 4");
+    if (g.block_size != 16) return fail(CWSL_ERR_INVALID, "the STFT channelizer is built for 192 kHz receivers");
+    if (window) {
+        const std::vector<float> w = cwsl::chan_window(g, cwsl::kChanKernelWidth);
+        std::memcpy(window, w.data(), w.size() * sizeof(float));
+    }
+    if (twiddle) {
+        const std::vector<std::complex<float>> tw = cwsl::chan_twiddles();
+        for (size_t i = 0; i < tw.size(); ++i) {
+            twiddle[2 * i] = tw[i].real();
+            twiddle[2 * i + 1] = tw[i].imag();
+        }
+    }
+    return CWSL_OK;
+}
+
+int cwsl_stft_channel(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, int32_t* q0, float* wgt, float* rot) {
+    cwsl::SsbdGeometry g;
+    if (!cwsl::ssbd_geometry(sample_rate, &g)) return fail(CWSL_ERR_INVALID, "Fs/B must be an even integer >= 4");
+    if (g.block_size != 16) return fail(CWSL_ERR_INVALID, "the STFT channelizer is built for 192 kHz receivers");
+    cwsl::NcoTables t;
+    if (!cwsl::nco_tables(g, demod_freq_hz, is_usb != 0, &t)) return fail(CWSL_ERR_INVALID, "Signal outside of band");
+    const cwsl::ChanChannel c = cwsl::chan_channel(g, t, cwsl::kChanKernelWidth, cwsl::kChanTaps);
+    if (q0) *q0 = c.q0;
+    if (wgt) std::memcpy(wgt, c.wgt.data(), c.wgt.size() * sizeof(float));
+    if (rot) {
+        rot[0] = c.rot.real();
+        rot[1] = c.rot.imag();
+    }
+    return CWSL_OK;
+}
+
 size_t cwsl_af_size(double period_s) { return cwsl::af_size(static_cast<float>(period_s)); }
 
 size_t cwsl_accepted_blocks(size_t n_iq_blocks, uint32_t iq_len, uint32_t sample_rate, size_t af_size) {

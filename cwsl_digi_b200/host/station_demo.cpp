@@ -40,11 +40,12 @@ private:
 
 int main(int argc, char** argv) {
     if (argc < 3) {
-        std::fprintf(stderr, "usage: %s <config.ini> <out_dir> [slots] [exact|fast]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s <config.ini> <out_dir> [slots] [exact|fast|stft]\n", argv[0]);
         return 2;
     }
     const int slots = argc > 3 ? std::atoi(argv[3]) : 2;
-    const int mode = (argc > 4 && std::string(argv[4]) == "exact") ? CWSL_MODE_EXACT : CWSL_MODE_FAST;
+    const std::string modeArg = argc > 4 ? argv[4] : "fast";
+    const int mode = modeArg == "exact" ? CWSL_MODE_EXACT : modeArg == "stft" ? CWSL_MODE_STFT : CWSL_MODE_FAST;
     auto printer = std::make_shared<ScreenPrinter>(LOG_LEVEL::INFO);
     FrontEndConfig cfg;
     try {

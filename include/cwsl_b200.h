@@ -70,6 +70,17 @@ int cwsl_ssbd_params(uint32_t sample_rate, uint32_t out[9]);
 int cwsl_build_tables(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, float* filter,
                       float* tone, float* phase_inc);
 
+/* Host-side constants of CWSL_MODE_STFT, for tests and diagnostics (no device needed; 192 kHz receivers only).
+ * window[512]      low-pass taps divided by the transform of the interpolation kernel;
+ * twiddle[2*1024]  (re,im) of W1024^(j2*q1) * i^q1 at [q1*32 + j2], the inter-pass factors of the 32x32 FFT;
+ * per channel: q0 = first (even) grid bin of the 8-bin stencil, wgt[8] its real interpolation weights,
+ * rot[2] = e^{-i 240 w}, w = the channel's NCO step per input sample. Any output pointer may be NULL.
+ * audio[b] = Weaver select of  phase[b] * rot * sum_i wgt[i] * X_b[(q0+i) mod 1024],  X_b[q] = i^q * FFT1024 of
+ * (window * the last 512 IQ samples up to and including SSBD block b). */
+int cwsl_stft_tables(uint32_t sample_rate, float* window, float* twiddle);
+int cwsl_stft_channel(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, int32_t* q0, float* wgt,
+                      float* rot);
+
 /* (period + 5 s) * 12000: length of one decoder's audio buffer, source/Instance.cpp:149. */
 size_t cwsl_af_size(double period_s);
 

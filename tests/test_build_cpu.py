@@ -53,3 +53,22 @@ def test_fast_kernel_is_ffma2_tma_and_spill_free(cw):
     assert len(imm) > 300                               # taps are FFMA2 immediates: no loads in the inner product
     tiled = [v for k, v in funcs.items() if "demod_exact_tiled_kernelILi16" in k][0]
     assert "UBLKCP" in _ops(tiled)
+
+
+def test_channelizer_kernel_shape(cw):
+    """STFT channelizer: packed FP32 butterflies, 128-bit spectrum reads, one 256-bit store per channel and batch,
+    named-barrier hand-over between the FFT warps and the interpolation warps, no spills, and few enough registers
+    (<= 104 x 512 threads) that one CTA of the quantise kernel fits beside it on every SM."""
+    funcs = _sass(cw)
+    chan = {k: v for k, v in funcs.items() if "demod_chan_kernel" in k}
+    assert len(chan) == 4                               # 1..4 channels per interpolation thread
+    for name, body in chan.items():
+        ops = _ops(body)
+        assert ops.count("FADD2") > 100 and ops.count("FFMA2") >= 8
+        assert any(i.startswith("LDS.128") for i in body)
+        assert any(".256" in i and i.startswith("STG") for i in body)
+        assert any(i.startswith("BAR.ARV") for i in body) and any(i.startswith("BAR.SYNC") for i in body)
+        assert "LDL" not in ops and "STL" not in ops
+    res = subprocess.run(["cuobjdump", "-res-usage", cw.lib_path()], capture_output=True, text=True, check=True).stdout
+    regs = [int(m.group(1)) for m in re.finditer(r"demod_chan_kernel.*?\n.*?REG:(\d+)", res)]
+    assert regs and max(regs) <= 104

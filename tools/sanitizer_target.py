@@ -1,9 +1,10 @@
-"""Small target for compute-sanitizer (memcheck / racecheck / synccheck): both kernels, several tiles and
-segments, channel groups, ring wrap, partial last tile."""
+"""Small target for compute-sanitizer (memcheck / racecheck / synccheck): all three demodulator kernels, several
+tiles and segments, channel groups, ring wrap, partial last tile / batch."""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("CWSL_STFT_MIN_CHANNELS", "1")
 import numpy as np
 
 import cwsl_digi_b200 as cw
@@ -12,7 +13,7 @@ from cwsl_digi_b200 import synth
 FS, IQ_LEN = 192000, 2048
 freqs = [int(f) for f in synth.stress_demod_freqs(40)]          # 2 channel groups (32 + 8)
 iq = synth.receiver_iq(70 * IQ_LEN, FS, freqs[:2], receiver=0, tones_per_channel=1)
-for mode in (cw.MODE_FAST, cw.MODE_EXACT):
+for mode in (cw.MODE_FAST, cw.MODE_EXACT, cw.MODE_STFT):
     with cw.Receiver(0, FS, IQ_LEN, ring_seconds=0.3, mode=mode) as rx:
         g = rx.add_group(15.0)
         for f in freqs:
