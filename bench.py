@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-station", action="store_true")
+    ap.add_argument("--no-other-modes", action="store_true",
+                    help="skip the short legs that time the other two arithmetic modes and check parity against EXACT")
     ap.add_argument("--per-receiver-streams", action="store_true",
                     help="resident arm: one CUDA stream per receiver (quantise of receiver r overlaps demod of r+1: "
                          "+2 %% throughput, but per-kernel event timings then overlap and the roofline figures are void)")
@@ -229,19 +231,26 @@ def run_b200(a):
     freqs = synth.stress_demod_freqs(a.channels)
     afs = cw.af_size(PERIOD)
 
-    # synthetic IQ, one distinct array per receiver (seed 20261017 + receiver id), generated on the device
+    # Synthetic IQ, one distinct array per receiver (seed 20261017 + receiver id), generated on the
+    # device: complex white noise, sigma 300 per component, plus 8 complex tones of amplitude 8000 inside every
+    # decoder passband at audio offsets drawn uniformly in [200, 2900] Hz (8192 tones at 1024 channels). The tones
+    # are synthesised with one inverse FFT of slot length (their frequencies sit on its 0.067 Hz grid).
+    rng = np.random.default_rng(synth.BASE_SEED)
+    tone_hz = (freqs[:, None].astype(np.float64) + rng.uniform(200.0, 2900.0, (a.channels, 8))).reshape(-1)
+    tone_bin = torch.from_numpy(np.mod(np.rint(tone_hz * n_iq / FS).astype(np.int64), n_iq)).cuda()
     iq_dev = []
-    t = torch.arange(n_iq, device="cuda", dtype=torch.float64)
     for r in my_rx:
         g = torch.Generator(device="cuda").manual_seed(synth.BASE_SEED + r)
+        ph = torch.rand(tone_bin.numel(), device="cuda", generator=g, dtype=torch.float64) * (2 * np.pi)
+        spec = torch.zeros(n_iq, device="cuda", dtype=torch.complex64)
+        spec.index_add_(0, tone_bin, (8000.0 * torch.exp(1j * ph)).to(torch.complex64))
+        z = torch.fft.ifft(spec, norm="forward")            # sum of the tones, no 1/n
         x = torch.randn(2 * n_iq, device="cuda", generator=g) * 300.0
-        for j in range(4):
-            f = -90000 + 45000 * j + 1234 + 17 * r
-            ph = 2 * np.pi * ((f * t) % FS) / FS
-            x[0::2] += (4000 * torch.cos(ph)).float()
-            x[1::2] += (4000 * torch.sin(ph)).float()
+        x[0::2] += z.real
+        x[1::2] += z.imag
         iq_dev.append(x.contiguous())
-    del t
+        del spec, z, ph
+    torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
     rxs = []
@@ -366,6 +375,63 @@ def run_b200(a):
                         "every H2D and D2H copy; wall clock around a device synchronize, max over ranks; "
                         f"{NBUF} pinned hand-off buffers in rotation")
 
+    # ---- the other arithmetic modes on the same receivers + in-run parity against the bit-exact mode ----------
+    other_modes, parity = {}, None
+    if not a.no_other_modes and not a.per_receiver_streams:
+        modes = {"stft": cw.MODE_STFT, "fast": cw.MODE_FAST, "exact": cw.MODE_EXACT}
+        for rx in rxs:
+            rx.synchronize()
+            rx.set_stream(stream.cuda_stream)
+        for name, m in modes.items():
+            if name == a.mode:
+                continue
+            for rx in rxs:
+                rx.set_mode(m)
+            step_resident()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            step_resident()
+            step_resident()
+            f1.record(stream)
+            barrier()
+            tm = torch.tensor([f0.elapsed_time(f1) / 2], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            other_modes[name] = dict(value=chs_step_total / (float(tm.item()) * 1e-3) / 1e6, unit=UNIT,
+                                     ms_per_step=float(tm.item()), steps=2)
+        if rank == 0:
+            # receiver 0 of this rank, every channel, on the bench's own IQ: int16 of each mode against the EXACT
+            # mode's (which the GPU tests pin bit-for-bit to the reference chain); float residual on 32 channels
+            rx0, sel = rxs[0], list(range(0, a.channels, max(1, a.channels // 32)))
+            got = {}
+            for name, m in modes.items():
+                rx0.set_mode(m)
+                rx0.bind_device_iq(iq_dev[0].data_ptr(), n_blocks)
+                rx0.end_slot(0, None)
+                rx0.synchronize()
+                q = torch.empty((a.channels, afs), dtype=torch.int16, device="cuda")
+                for c in range(a.channels):
+                    rx0.copy_device_audio(0, c, q[c].data_ptr())
+                rx0.synchronize()
+                got[name] = (q, {c: rx0.read_float_audio(0, c) for c in sel})
+            parity = {"reference": "EXACT mode (bit-identical to the reference chain, tests/test_parity_gpu.py)",
+                      "input": "receiver 0 of this run, all channels (int16) / every 32nd channel (float residual)"}
+            wi = n_blocks * IQ_LEN // 16
+            for name in ("fast", "stft"):
+                d = (got[name][0].to(torch.int32) - got["exact"][0].to(torch.int32)).abs()
+                worst = -1e9
+                for c in sel:
+                    want = got["exact"][1][c][:wi].astype(np.float64)
+                    err = got[name][1][c][:wi].astype(np.float64) - want
+                    worst = max(worst, 20 * np.log10(max(np.sqrt(np.mean(err ** 2)), 1e-300) / np.sqrt(np.mean(want ** 2))))
+                parity[name] = dict(max_int16_lsb=int(d.max().item()), differing_samples=float((d > 0).float().mean().item()),
+                                    worst_residual_db=float(worst))
+            del got
+        for rx in rxs:
+            rx.set_mode(mode)
+            rx.synchronize()
+
     # ---- BASELINE.json configs[2]: the 8-receiver x 7-mode skimmer station, streamed ----------------------
     station = None
     if not a.no_station:
@@ -470,6 +536,7 @@ def run_b200(a):
                     data="synthetic",
                     config=dict(workload=workload_name(a), receivers_total=a.receivers, channels=a.channels,
                                 receivers_per_rank=len(my_rx), sample_rate=FS, iq_len=IQ_LEN, slot_s=PERIOD,
+                                input="SURVEY.md 8d: complex noise sigma 300 + 8 tones of amplitude 8000 in every decoder passband",
                                 mode=a.mode, parallelism=f"receiver-sharded x{world}, no data-path collective",
                                 streams="one CUDA stream per receiver, forked from / joined into the timed master stream"
                                         if a.per_receiver_streams else "one stream for all receivers of the rank",
@@ -479,7 +546,7 @@ def run_b200(a):
                     gchs_per_gpu=value / 1e3 / world,
                     clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                     kernel_ms=dict(demod=demod_ms, quantise_and_clear=quant_ms, event_total=ms_total),
-                    station=station,
+                    station=station, other_modes=other_modes, parity_in_run=parity,
                     gathered_checksums=gathered)
         print(json.dumps(line), flush=True)
     for rx in rxs:
