@@ -103,7 +103,8 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
 }
 
 // named barriers (0 is __syncthreads): spectrum buffer s is FULL / EMPTY
-constexpr int kBarFull = 1, kBarEmpty = 3;
+constexpr int kBufs = 3;          // spectrum buffers in flight between the FFT warps and the interpolation warps
+constexpr int kBarFull = 1, kBarEmpty = 1 + kBufs;
 __device__ __forceinline__ void bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -121,7 +122,7 @@ constexpr int kFftThreads = 32 * kHB;
 constexpr int kIntThreads = 256;  // interpolation threads per CTA, each owns up to KC channels for the whole launch
 constexpr int kThreads = kFftThreads + kIntThreads;
 constexpr int kAnchorEvery = 16;  // batches between re-reads of the exact phase table (the recurrence runs in between)
-constexpr size_t kSpecBytes = (size_t)2 * kHB * kHopStride * 8;  // double-buffered spectra
+constexpr size_t kSpecBytes = (size_t)kBufs * kHB * kHopStride * 8;  // 3 x 8 x 8.25 KB = 198 KB
 
 // Persistent, warp-specialised: CTA j owns a contiguous run of batches (kHB hops each). Warps 0..7 (producers) each
 // compute the 1024-point spectrum of one hop of the batch into spectrum buffer s = batch & 1; warps 8..15
@@ -152,9 +153,9 @@ __global__ void __maxnreg__(104)
         float wv[16];  // this lane's 16 window taps (constant over the launch)
 #pragma unroll
         for (int j1 = 0; j1 < 16; ++j1) wv[j1] = __ldg(c.window + 32 * j1 + lane);
-        for (uint32_t i = s0; i < s1; ++i) {
-            const uint32_t s = (i - s0) & 1u;
-            if (i - s0 >= 2) bar_sync(kBarEmpty + s, kThreads);  // consumers are done with this buffer
+        uint32_t s = 0;
+        for (uint32_t i = s0; i < s1; ++i, s = (s + 1 == (uint32_t)kBufs) ? 0u : s + 1) {
+            if (i - s0 >= (uint32_t)kBufs) bar_sync(kBarEmpty + s, kThreads);  // consumers are done with this buffer
             float2* buf = spec + (size_t)(s * kHB + warp) * kHopStride;
             float2 v[32];
             // pass 1: lane = j2, 32-point DFT over j1 of u[32 j1 + j2], u = x * window (j1 >= 16 is the zero padding)
@@ -213,8 +214,8 @@ __global__ void __maxnreg__(104)
             mx[k] = 0.0f;
         }
         const unsigned char* spec_b = smem;
-        for (uint32_t i = s0; i < s1; ++i) {
-            const uint32_t s = (i - s0) & 1u;
+        uint32_t s = 0;
+        for (uint32_t i = s0; i < s1; ++i, s = (s + 1 == (uint32_t)kBufs) ? 0u : s + 1) {
             const uint32_t bb = p.b0 + i * kHB;
             const bool anchor = ((i - s0) % kAnchorEvery) == 0;
             if (anchor) {
@@ -270,7 +271,7 @@ __global__ void __maxnreg__(104)
                     }
                 }
             }
-            if (i + 2 < s1) bar_arrive(kBarEmpty + s, kThreads);  // (nobody waits for the last two)
+            if (i + kBufs < s1) bar_arrive(kBarEmpty + s, kThreads);  // (nobody waits for the last ones)
         }
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
