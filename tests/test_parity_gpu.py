@@ -126,11 +126,11 @@ def test_config1_full_ft8_slot(gpu, ref, mode):
 
 # ---- streaming: chunked pushes through a small ring == one shot ---------------------------------
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("fs,iq_len", [(192000, 2048), (192000, 512), (96000, 1024), (48000, 512)])
+@pytest.mark.parametrize("fs,iq_len", [(192000, 2048), (192000, 512), (192000, 64), (96000, 1024), (48000, 512)])
 def test_streaming_small_ring(gpu, ref, mode, fs, iq_len):
     cw = gpu
     freq = -fs // 8
-    nblk = 3 * fs // iq_len
+    nblk = (3 * fs if iq_len >= 512 else fs // 2) // iq_len     # (iq_len 64: launches start at odd multiples of 4 blocks)
     iq = synth.receiver_iq(nblk * iq_len, fs, [freq], receiver=5, tones_per_channel=2)
     rng = np.random.default_rng(iq_len)
     chunks = list(rng.integers(1, 12, 2000))
