@@ -483,6 +483,25 @@ def test_stress_stft_channelizer(stress_run, ref):
         assert r <= -85.0      # noise-only channels 47 dB under the band's tones, see above; the int16 bar holds
 
 
+def test_stft_more_channels_than_one_launch(stress_run):
+    """1100 channels: the channelizer runs two launches (1024 + 76 channels, offset pointers); every channel within
+    2 LSB of the direct-form FAST kernel (each is within 1 LSB of the reference)."""
+    s = stress_run
+    cw, x, fs, iq_len, nblk = s["cw"], s["x"], s["fs"], s["iq_len"], s["nblk"]
+    freqs = synth.stress_demod_freqs(1100)
+    outs = {}
+    for mode in (cw.MODE_FAST, cw.MODE_STFT):
+        with cw.Receiver(0, fs, iq_len, mode=mode) as rx:
+            grp = rx.add_group(15.0)
+            for f in freqs:
+                rx.add_channel(grp, int(f), 0.9)
+            rx.bind_device_iq(x.data_ptr(), nblk)
+            outs[mode], wi = rx.end_slot_numpy(grp)
+    d = np.abs(outs[cw.MODE_STFT].astype(np.int32) - outs[cw.MODE_FAST].astype(np.int32))
+    assert wi == 179968 and d.max() <= 2 * FAST_MAX_LSB
+    assert d[1024:].max() <= 2 * FAST_MAX_LSB and np.abs(outs[cw.MODE_STFT][1024:]).max() > 20000
+
+
 def test_stress_exact_spot_channels(stress_run, ref):
     s = stress_run
     cw, freqs, x, nblk, fs, iq_len = s["cw"], s["freqs"], s["x"], s["nblk"], s["fs"], s["iq_len"]
