@@ -41,7 +41,8 @@ namespace {
 
 constexpr int kN = 1024;         // FFT size (512-tap window, oversampling 2)
 constexpr int kL = 512;          // window length = FiltOrder at 192 kHz
-constexpr int kHopStride = 1056; // float2 per hop buffer: 32 rows of 33 during the transpose, 1024 bins after
+constexpr int kRow = 34;          // float2 per transpose row: conflict-free 64-bit column writes AND 128-bit row reads
+constexpr int kHopStride = 32 * kRow;  // float2 per hop buffer: 32 rows of 34 during the transpose, 1024 (+8) bins after
 
 // W32^k = exp(-2 pi i k / 32), k = 0..15
 __device__ __forceinline__ float2 mul_w32(float2 d, int k) {
@@ -122,7 +123,7 @@ constexpr int kFftThreads = 32 * kHB;
 constexpr int kIntThreads = 256;  // interpolation threads per CTA, each owns up to KC channels for the whole launch
 constexpr int kThreads = kFftThreads + kIntThreads;
 constexpr int kAnchorEvery = 16;  // batches between re-reads of the exact phase table (the recurrence runs in between)
-constexpr size_t kSpecBytes = (size_t)kBufs * kHB * kHopStride * 8;  // 3 x 8 x 8.25 KB = 198 KB
+constexpr size_t kSpecBytes = (size_t)kBufs * kHB * kHopStride * 8;  // 3 x 8 x 8.5 KB = 204 KB
 
 // Persistent, warp-specialised: CTA j owns a contiguous run of batches (kHB hops each). Warps 0..7 (producers) each
 // compute the 1024-point spectrum of one hop of the batch into spectrum buffer s = batch & 1; warps 8..15
@@ -168,18 +169,22 @@ __global__ void __maxnreg__(104)
                 v[j1] = fmul2(x, bc(wv[j1]));
             }
             fft32<true>(v);
-            // twiddle W1024^(j2 q1) * i^q1 and transpose through the hop buffer (rows of 33: conflict-free both ways)
+            // twiddle W1024^(j2 q1) * i^q1 and transpose through the hop buffer (rows of 34: conflict-free both ways)
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 const int q1 = bitrev5(k);
                 const float2 w = __ldg(c.twiddle + 32 * q1 + lane);
                 const float2 a = v[k];
-                buf[q1 * 33 + lane] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+                buf[q1 * kRow + lane] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
             }
             __syncwarp();
             // pass 2: lane = q1, 32-point DFT over j2 -> bins q1 + 32 q2
 #pragma unroll
-            for (int j2 = 0; j2 < 32; ++j2) v[j2] = buf[lane * 33 + j2];
+            for (int j2 = 0; j2 < 32; j2 += 2) {
+                const float4 two = *reinterpret_cast<const float4*>(buf + lane * kRow + j2);
+                v[j2] = make_float2(two.x, two.y);
+                v[j2 + 1] = make_float2(two.z, two.w);
+            }
             __syncwarp();
             fft32<false>(v);
 #pragma unroll
