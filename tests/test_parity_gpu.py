@@ -173,6 +173,34 @@ def test_consecutive_slots_and_two_groups(gpu, ref):
         assert wi == o["write_index"] and np.array_equal(out[0], o["i16"])
 
 
+def test_mode_switch_between_slots_and_stft_slot_purity(gpu, ref):
+    """One receiver, five consecutive slots with the arithmetic mode changed at the slot edges
+    (STFT, STFT, FAST, EXACT, STFT): every slot starts from fresh SSBD state (Instance.cpp:251; for STFT: zero
+    history in the first 31 hops and a phase anchor at the first hop of every launch), and the float scratch / int16 of
+    each slot meet that mode's bars. Each slot is demodulated in two launches (cwsl_rx_process in the middle)."""
+    cw = gpu
+    fs, iq_len, unit = 192000, 2048, 24
+    chans = [(-26000, 0.9), (12345, 0.2), (89000, 0.9)]
+    plan = [cw.MODE_STFT, cw.MODE_STFT, cw.MODE_FAST, cw.MODE_EXACT, cw.MODE_STFT]
+    iq = synth.receiver_iq(len(plan) * unit * iq_len, fs, [c[0] for c in chans], receiver=11, tones_per_channel=2)
+    with cw.Receiver(0, fs, iq_len, ring_seconds=0.5, mode=plan[0]) as rx:
+        g = rx.add_group(15.0)
+        for f, sc in chans:
+            rx.add_channel(g, f, sc)
+        for i, m in enumerate(plan):
+            rx.set_mode(m)
+            span = iq[i * unit * iq_len * 2:(i + 1) * unit * iq_len * 2]
+            half = (unit // 2) * iq_len * 2
+            rx.push_iq(span[:half])
+            rx.process(g)
+            rx.push_iq(span[half:])
+            out, wi = rx.end_slot_numpy(g)
+            raw = np.stack([rx.read_float_audio(g, c) for c in range(len(chans))])
+            stats = [rx.channel_stats(g, c) for c in range(len(chans))]
+            want = [ref.slot(fs, f, span, iq_len, sc, af_size(15)) for f, sc in chans]
+            (check_exact if m == cw.MODE_EXACT else check_fast)(out, raw, wi, stats, want)
+
+
 def test_empty_slot_is_all_zero(gpu):
     cw = gpu
     with cw.Receiver(0, 192000, 2048, mode=cw.MODE_FAST) as rx:
