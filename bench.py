@@ -252,7 +252,14 @@ def run_b200(a):
         del spec, z, ph
     torch.cuda.synchronize()
 
-    stream = torch.cuda.current_stream()
+    # The compute stream is a HIGH-priority stream: the receivers' post streams (quantise, D2H) are created with the
+    # lowest priority by the library, so a demodulation that becomes runnable together with the previous receiver's
+    # quantise pass gets its CTAs placed first and the quantise CTAs fill the rest of each SM.
+    try:
+        stream = torch.cuda.Stream(priority=-1)
+    except Exception:  # noqa: BLE001
+        stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     rxs = []
     for _ in my_rx:
         rx = cw.Receiver(local, FS, IQ_LEN, mode=mode)
@@ -356,7 +363,10 @@ def run_b200(a):
         # Kernels of all receivers are queued FIFO on ONE compute stream (so receivers finish one after the other,
         # not all together), the H2D of the next receiver's IQ rides the same stream, and every finished slot is
         # copied back on its receiver's private copy stream (inside cwsl_rx_end_slot), overlapping the next kernels.
-        e2e_stream = torch.cuda.Stream()
+        try:
+            e2e_stream = torch.cuda.Stream(priority=-1)
+        except Exception:  # noqa: BLE001
+            e2e_stream = torch.cuda.Stream()
         for rx in rxs:
             rx.set_stream(e2e_stream.cuda_stream)
         checks = [0]

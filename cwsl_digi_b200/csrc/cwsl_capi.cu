@@ -636,8 +636,13 @@ cwsl_rx_t* cwsl_rx_create(int device, uint32_t sample_rate, uint32_t iq_len, dou
     rx->geo = geo;
     rx->sub = iq_len / geo.block_size;
     rx->ring_seconds = ring_seconds;
-    if (cudaStreamCreateWithFlags(&rx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&rx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // The post stream (normalise/quantise, max reset, D2H) gets the LOWEST priority: when its quantise kernel and the
+    // next demodulation become runnable together, the block scheduler places the demodulator's CTAs first and the
+    // HBM-bound quantise CTAs fill what is left of every SM, instead of the demodulator waiting for them to drain.
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&rx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&rx->copy_stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaEventCreateWithFlags(&rx->ev_out_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&rx->ev_d2h_done, cudaEventDisableTiming) != cudaSuccess) {
         fail(CWSL_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
