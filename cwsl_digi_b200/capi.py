@@ -138,11 +138,14 @@ def build_tables(fs: int, demod_freq: int, is_usb: bool = True) -> dict:
 
 
 def stft_tables(fs: int = 192000) -> dict:
-    """Host-side shared tables of CWSL_MODE_STFT: deconvolved window [512], FFT twiddles complex64 [32, 32]."""
-    w = np.zeros(512, np.float32)
-    tw = np.zeros(2 * 1024, np.float32)
+    """Host-side shared tables of CWSL_MODE_STFT: deconvolved window [L = FiltOrder], FFT twiddles complex64
+    [N/32, 32] with N = 2 L (1024 / 512 / 256 bins at 192 / 96 / 48 kHz)."""
+    n_taps = ssbd_params(fs)["FiltOrder"]
+    a = 2 * n_taps // 32
+    w = np.zeros(n_taps, np.float32)
+    tw = np.zeros(2 * a * 32, np.float32)
     _check(lib().cwsl_stft_tables(fs, w.ctypes.data, tw.ctypes.data))
-    return dict(window=w, twiddle=tw.view(np.complex64).reshape(32, 32))
+    return dict(window=w, twiddle=tw.view(np.complex64).reshape(a, 32), grid=2 * n_taps)
 
 
 def stft_channel(fs: int, demod_freq: int, is_usb: bool = True) -> dict:

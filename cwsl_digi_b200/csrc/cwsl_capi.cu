@@ -65,7 +65,7 @@ struct ChanDeviceTables {  // STFT channelizer: deconvolved window and FFT twidd
     float* window = nullptr;
     float2* twiddle = nullptr;
 };
-std::map<int, ChanDeviceTables> g_chan_tables;
+std::map<std::pair<int, uint32_t>, ChanDeviceTables> g_chan_tables;  // per (device, block size)
 
 // Managed hand-off buffers (cwsl_host_alloc): pinned, zero-initialised, and only ever written by
 // cwsl_rx_end_slot, so the library knows which columns of a destination can hold non-zero data and
@@ -240,17 +240,17 @@ int commit_impl(cwsl_rx* rx) {
             CK(cwsl::upload_taps(rx->geo.block_size, h.data()));
             g_taps_uploaded.insert(key);
         }
-        if (rx->geo.block_size == 16 && !g_chan_tables.count(rx->device)) {  // STFT window + FFT twiddles, once per device
+        if (!g_chan_tables.count(key)) {  // STFT window + FFT twiddles, once per device and rate
             const std::vector<float> w = cwsl::chan_window(rx->geo, cwsl::kChanKernelWidth);
-            const std::vector<std::complex<float>> tw = cwsl::chan_twiddles();
+            const std::vector<std::complex<float>> tw = cwsl::chan_twiddles(rx->geo);
             ChanDeviceTables t;
             CK(cudaMalloc(&t.window, w.size() * sizeof(float)));
             CK(cudaMalloc(&t.twiddle, tw.size() * sizeof(float2)));
             CK(cudaMemcpy(t.window, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(t.twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-            g_chan_tables[rx->device] = t;
+            g_chan_tables[key] = t;
         }
-        if (rx->geo.block_size == 16) rx->chan_tables = g_chan_tables[rx->device];
+        rx->chan_tables = g_chan_tables[key];
     }
     uint64_t max_blocks = 0;
     for (Group& g : rx->groups) {
@@ -281,7 +281,7 @@ int commit_impl(cwsl_rx* rx) {
         CK(cudaMemcpyAsync(g.d_scale, scale.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
         CK(cudaMemsetAsync(g.d_maxbits, 0, C * sizeof(unsigned), rx->stream));
         std::vector<cwsl::ChanConst> cconst;
-        if (BS == 16) {  // STFT channelizer constants (CWSL_MODE_STFT)
+        {  // STFT channelizer constants (CWSL_MODE_STFT)
             cconst.resize(C);
             for (uint32_t c = 0; c < C; ++c) {
                 const cwsl::ChanChannel cc = cwsl::chan_channel(rx->geo, g.ch[c].nco, cwsl::kChanKernelWidth, cwsl::kChanTaps);
@@ -432,7 +432,7 @@ int process_group(cwsl_rx* rx, Group& g) {
         else
             CK(cwsl::launch_demod_exact(p, rx->stream));
     }
-    else if (rx->mode == CWSL_MODE_STFT && p.block_size == 16 && p.n_channels >= stft_min_channels()) {
+    else if (rx->mode == CWSL_MODE_STFT && p.n_channels >= stft_min_channels()) {
         // big channel groups: one FFT per hop shared by all channels, <= kChanMaxChannels channels per launch
         for (uint32_t c0 = 0; c0 < p.n_channels; c0 += cwsl::kChanMaxChannels) {
             cwsl::DemodLaunch q = p;
@@ -558,13 +558,14 @@ int cwsl_build_tables(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, f
 int cwsl_stft_tables(uint32_t sample_rate, float* window, float* twiddle) {
     cwsl::SsbdGeometry g;
     if (!cwsl::ssbd_geometry(sample_rate, &g)) return fail(CWSL_ERR_INVALID, "Fs/B must be an even integer >= 4");
-    if (g.block_size != 16) return fail(CWSL_ERR_INVALID, "the STFT channelizer is built for 192 kHz receivers");
+    if (g.block_size != 16 && g.block_size != 8 && g.block_size != 4)
+        return fail(CWSL_ERR_INVALID, "the STFT channelizer is built for 192, 96 and 48 kHz receivers");
     if (window) {
         const std::vector<float> w = cwsl::chan_window(g, cwsl::kChanKernelWidth);
         std::memcpy(window, w.data(), w.size() * sizeof(float));
     }
     if (twiddle) {
-        const std::vector<std::complex<float>> tw = cwsl::chan_twiddles();
+        const std::vector<std::complex<float>> tw = cwsl::chan_twiddles(g);
         for (size_t i = 0; i < tw.size(); ++i) {
             twiddle[2 * i] = tw[i].real();
             twiddle[2 * i + 1] = tw[i].imag();
@@ -576,7 +577,8 @@ int cwsl_stft_tables(uint32_t sample_rate, float* window, float* twiddle) {
 int cwsl_stft_channel(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, int32_t* q0, float* wgt, float* rot) {
     cwsl::SsbdGeometry g;
     if (!cwsl::ssbd_geometry(sample_rate, &g)) return fail(CWSL_ERR_INVALID, "Fs/B must be an even integer >= 4");
-    if (g.block_size != 16) return fail(CWSL_ERR_INVALID, "the STFT channelizer is built for 192 kHz receivers");
+    if (g.block_size != 16 && g.block_size != 8 && g.block_size != 4)
+        return fail(CWSL_ERR_INVALID, "the STFT channelizer is built for 192, 96 and 48 kHz receivers");
     cwsl::NcoTables t;
     if (!cwsl::nco_tables(g, demod_freq_hz, is_usb != 0, &t)) return fail(CWSL_ERR_INVALID, "Signal outside of band");
     const cwsl::ChanChannel c = cwsl::chan_channel(g, t, cwsl::kChanKernelWidth, cwsl::kChanTaps);

@@ -39,10 +39,24 @@ namespace cwsl {
 
 namespace {
 
-constexpr int kN = 1024;         // FFT size (512-tap window, oversampling 2)
-constexpr int kL = 512;          // window length = FiltOrder at 192 kHz
-constexpr int kRow = 34;          // float2 per transpose row: conflict-free 64-bit column writes AND 128-bit row reads
-constexpr int kHopStride = 32 * kRow;  // float2 per hop buffer: 32 rows of 34 during the transpose, 1024 (+8) bins after
+constexpr int kRow = 34;  // float2 per transpose row: conflict-free 64-bit column writes AND 128-bit row reads
+
+// Geometry per receiver rate: window L = FiltOrder = 32 * BS taps, grid N = 2 L, FFT as A x 32 with A = N / 32.
+// One warp transforms HW = 32 / A hops at a time (pass 1: every lane runs HW A-point DFTs; pass 2: lane -> (hop,
+// q1), one 32-point DFT each), so all 32 lanes are busy in both passes at every rate.
+template <int BS>
+struct ChanGeo {
+    static constexpr int kL = 32 * BS;       // 512 / 256 / 128
+    static constexpr int kN = 2 * kL;        // 1024 / 512 / 256
+    static constexpr int kA = kN / 32;       // 32 / 16 / 8
+    static constexpr int kHW = 32 / kA;      // hops per warp and batch: 1 / 2 / 4
+    static constexpr int kHB = 8 * kHW;      // hops per batch (8 FFT warps): 8 / 16 / 32
+    // float2 per hop buffer: A rows of 34 during the transpose, N (+8 wrapped) bins after; the 8-row geometry gets 8
+    // more so that the two hops of a half-warp sit 16 banks apart
+    static constexpr int kHop = kA * kRow + (kA == 8 ? 8 : 0);
+    static constexpr int kAnchorEvery = 16 / kHW;  // batches between phase-table anchors (128 hops)
+    static_assert(kN + 8 <= kHop, "wrapped stencil bins must fit");
+};
 
 // W32^k = exp(-2 pi i k / 32), k = 0..15
 __device__ __forceinline__ float2 mul_w32(float2 d, int k) {
@@ -70,36 +84,52 @@ __device__ __forceinline__ float2 mul_w32(float2 d, int k) {
     }
 }
 
-__host__ __device__ constexpr int bitrev5(int i) {
-    return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+
+template <int A>
+__host__ __device__ constexpr int bitrev(int i) {  // over log2(A) bits
+    int r = 0;
+    for (int b = 1, m = A >> 1; b < A; b <<= 1, m >>= 1)
+        if (i & b) r |= m;
+    return r;
 }
 
-// In-register 32-point forward DFT, radix-2 decimation in frequency; X[bitrev5(i)] is left in v[i].
-// UPPER_ZERO: v[16..31] are known zeros on entry (the zero-padded half of the window).
-template <bool UPPER_ZERO>
-__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+// In-register A-point forward DFT (A = 8, 16, 32) on v[OFF .. OFF+A), radix-2 decimation in frequency;
+// X[bitrev<A>(i)] is left in v[OFF + i]. UPPER_ZERO: v[OFF+A/2 .. OFF+A) are known zeros on entry (the zero-padded
+// half of the window). W_A^k = W32^(k * 32/A).
+template <int A, int OFF, bool UPPER_ZERO>
+__device__ __forceinline__ void fft_dif(float2 (&v)[32]) {
+    constexpr int H = A / 2;
     if constexpr (UPPER_ZERO) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k + 16] = mul_w32(v[k], k);
+        for (int k = 0; k < H; ++k) v[OFF + k + H] = mul_w32(v[OFF + k], k * (16 / H));
     } else {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float2 a = v[k], b = v[k + 16];
-            v[k] = fadd2(a, b);
-            v[k + 16] = mul_w32(fsub2(a, b), k);
+        for (int k = 0; k < H; ++k) {
+            const float2 a = v[OFF + k], b = v[OFF + k + H];
+            v[OFF + k] = fadd2(a, b);
+            v[OFF + k + H] = mul_w32(fsub2(a, b), k * (16 / H));
         }
     }
 #pragma unroll
-    for (int half = 8; half >= 1; half >>= 1) {
+    for (int half = H / 2; half >= 1; half >>= 1) {
 #pragma unroll
-        for (int g = 0; g < 32; g += 2 * half) {
+        for (int g = 0; g < A; g += 2 * half) {
 #pragma unroll
             for (int k = 0; k < half; ++k) {
-                const float2 a = v[g + k], b = v[g + k + half];
-                v[g + k] = fadd2(a, b);
-                v[g + k + half] = mul_w32(fsub2(a, b), k * (16 / half));
+                const float2 a = v[OFF + g + k], b = v[OFF + g + k + half];
+                v[OFF + g + k] = fadd2(a, b);
+                v[OFF + g + k + half] = mul_w32(fsub2(a, b), k * (16 / half));
             }
         }
+    }
+}
+template <int A, bool UPPER_ZERO>
+__device__ __forceinline__ void fft_dif_all(float2 (&v)[32]) {  // the 32/A transforms a lane holds in pass 1
+    fft_dif<A, 0, UPPER_ZERO>(v);
+    if constexpr (A <= 16) fft_dif<A, A, UPPER_ZERO>(v);
+    if constexpr (A <= 8) {
+        fft_dif<A, 2 * A, UPPER_ZERO>(v);
+        fft_dif<A, 3 * A, UPPER_ZERO>(v);
     }
 }
 
@@ -118,22 +148,26 @@ __device__ __forceinline__ void stg256(float* dst, const float (&o)[8]) {  // on
                  : "memory");
 }
 
-constexpr int kHB = 8;            // hops per batch = FFT warps per CTA
-constexpr int kFftThreads = 32 * kHB;
+constexpr int kFftWarps = 8;
+constexpr int kFftThreads = 32 * kFftWarps;
 constexpr int kIntThreads = 256;  // interpolation threads per CTA, each owns up to KC channels for the whole launch
 constexpr int kThreads = kFftThreads + kIntThreads;
-constexpr int kAnchorEvery = 16;  // batches between re-reads of the exact phase table (the recurrence runs in between)
-constexpr size_t kSpecBytes = (size_t)kBufs * kHB * kHopStride * 8;  // 3 x 8 x 8.5 KB = 204 KB
+template <int BS>
+constexpr size_t spec_bytes() {  // 3 buffers x (8 FFT warps x HW hops) x hop buffer: 204 KB at every rate
+    return (size_t)kBufs * ChanGeo<BS>::kHB * ChanGeo<BS>::kHop * 8;
+}
 
-// Persistent, warp-specialised: CTA j owns a contiguous run of batches (kHB hops each). Warps 0..7 (producers) each
-// compute the 1024-point spectrum of one hop of the batch into spectrum buffer s = batch & 1; warps 8..15
-// (consumers) read every channel's frequency off those spectra while the producers are already transforming the
-// next batch. Hand-over by named barriers (bar.arrive / bar.sync), no __syncthreads in the loop.
-template <int KC>
-// 104 registers x 512 threads leave room on every SM for one CTA of the (HBM-bound) quantise kernel of the previous
+// Persistent, warp-specialised: CTA j owns a contiguous run of batches (kHB hops each). Warps 0..7 (producers)
+// compute the spectra of the batch's hops into spectrum buffer s; warps 8..15 (consumers) read every channel's
+// frequency off those spectra while the producers are already transforming the next batches. Hand-over by named
+// barriers (bar.arrive / bar.sync), no __syncthreads in the loop.
+// 104 registers x 512 threads leave room on every SM for CTAs of the (HBM-bound) quantise kernel of the previous
 // receiver, which then runs underneath this (shared-memory-bound) kernel instead of after it.
+template <int BS, int KC>
 __global__ void __maxnreg__(104)
     demod_chan_kernel(DemodLaunch p, ChanLaunch c, uint32_t n_batches, uint32_t batches_per_cta) {
+    using G = ChanGeo<BS>;
+    constexpr int A = G::kA, HW = G::kHW, HB = G::kHB, HOP = G::kHop, N = G::kN;
     extern __shared__ __align__(16) unsigned char smem[];
     float2* spec = reinterpret_cast<float2*>(smem);
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
@@ -141,58 +175,69 @@ __global__ void __maxnreg__(104)
     const uint32_t s1 = min(n_batches, s0 + batches_per_cta);
     if (s0 >= s1) return;
 
-    if (warp < (uint32_t)kHB) {
-        // ================= producers: hop h = warp of every batch =================
-        // window of hop b = IQ blocks b-31 .. b; element j = 32 j1 + lane sits in block b-31 + 2 j1 + (lane >> 4)
-        long long blk = (long long)p.b0 + (long long)s0 * kHB + (long long)warp - 31 + (long long)(lane >> 4);
+    if (warp < (uint32_t)kFftWarps) {
+        // ================= producers: warp w transforms hops w*HW .. w*HW+HW-1 of every batch =================
+        // window of hop b = IQ blocks b-31 .. b (BS samples each); element j = 32 j1 + lane of the window sits in
+        // block b-31 + j1*(32/BS) + lane/BS, sample lane % BS
+        long long blk = (long long)p.b0 + (long long)s0 * HB + (long long)warp * HW - 31 + (long long)(lane / BS);
         uint32_t row;
         {
             long long m = ((long long)p.ring_off + blk) % (long long)p.ring_blocks;
             if (m < 0) m += p.ring_blocks;
             row = (uint32_t)m;
         }
-        float wv[16];  // this lane's 16 window taps (constant over the launch)
+        float wv[A / 2];  // this lane's window taps (constant over the launch)
 #pragma unroll
-        for (int j1 = 0; j1 < 16; ++j1) wv[j1] = __ldg(c.window + 32 * j1 + lane);
+        for (int j1 = 0; j1 < A / 2; ++j1) wv[j1] = __ldg(c.window + 32 * j1 + lane);
         uint32_t s = 0;
         for (uint32_t i = s0; i < s1; ++i, s = (s + 1 == (uint32_t)kBufs) ? 0u : s + 1) {
             if (i - s0 >= (uint32_t)kBufs) bar_sync(kBarEmpty + s, kThreads);  // consumers are done with this buffer
-            float2* buf = spec + (size_t)(s * kHB + warp) * kHopStride;
+            float2* wbuf = spec + ((size_t)s * HB + (size_t)warp * HW) * HOP;  // this warp's HW hop buffers
             float2 v[32];
-            // pass 1: lane = j2, 32-point DFT over j1 of u[32 j1 + j2], u = x * window (j1 >= 16 is the zero padding)
+            // pass 1: lane = j2; per hop an A-point DFT over j1 of u[32 j1 + j2], u = x * window (j1 >= A/2: zero padding)
 #pragma unroll
-            for (int j1 = 0; j1 < 16; ++j1) {
-                uint32_t r = row + 2 * j1;  // < 2 * ring_blocks
-                if (r >= p.ring_blocks) r -= p.ring_blocks;
-                float2 x = make_float2(0.0f, 0.0f);
-                if (blk + 2 * j1 >= 0) x = __ldg(p.iq_ring + (size_t)r * 16 + (lane & 15u));  // zero history before the slot
-                v[j1] = fmul2(x, bc(wv[j1]));
+            for (int sub = 0; sub < HW; ++sub) {
+#pragma unroll
+                for (int j1 = 0; j1 < A / 2; ++j1) {
+                    const int boff = sub + j1 * (32 / BS);     // block offset of this element from the lane's base block
+                    uint32_t r = row + boff;                   // < 2 * ring_blocks
+                    if (r >= p.ring_blocks) r -= p.ring_blocks;
+                    float2 x = make_float2(0.0f, 0.0f);
+                    if (blk + boff >= 0) x = __ldg(p.iq_ring + (size_t)r * BS + (lane % BS));  // zero history before the slot
+                    v[sub * A + j1] = fmul2(x, bc(wv[j1]));
+                }
             }
-            fft32<true>(v);
-            // twiddle W1024^(j2 q1) * i^q1 and transpose through the hop buffer (rows of 34: conflict-free both ways)
+            fft_dif_all<A, true>(v);
+            // twiddle W_N^(j2 q1) * i^q1 and transpose through the hop buffer (rows of 34: conflict-free both ways)
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const int q1 = bitrev5(k);
-                const float2 w = __ldg(c.twiddle + 32 * q1 + lane);
-                const float2 a = v[k];
-                buf[q1 * kRow + lane] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+            for (int sub = 0; sub < HW; ++sub) {
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    const int q1 = bitrev<A>(k);
+                    const float2 w = __ldg(c.twiddle + 32 * q1 + lane);
+                    const float2 a = v[sub * A + k];
+                    wbuf[sub * HOP + q1 * kRow + lane] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+                }
             }
             __syncwarp();
-            // pass 2: lane = q1, 32-point DFT over j2 -> bins q1 + 32 q2
+            // pass 2: lane -> (hop sub2, q1); 32-point DFT over j2 -> bins q1 + A q2 of that hop
+            const uint32_t sub2 = lane / A, q1 = lane % A;
+            float2* buf = wbuf + sub2 * HOP;
 #pragma unroll
             for (int j2 = 0; j2 < 32; j2 += 2) {
-                const float4 two = *reinterpret_cast<const float4*>(buf + lane * kRow + j2);
+                const float4 two = *reinterpret_cast<const float4*>(buf + q1 * kRow + j2);
                 v[j2] = make_float2(two.x, two.y);
                 v[j2 + 1] = make_float2(two.z, two.w);
             }
             __syncwarp();
-            fft32<false>(v);
+            fft_dif<32, 0, false>(v);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) buf[32 * bitrev5(k) + lane] = v[k];
-            if (lane < 8) buf[kN + lane] = v[0];  // bins 0..7 again behind bin 1023: stencils never wrap
+            for (int k = 0; k < 32; ++k) buf[A * bitrev<32>(k) + q1] = v[k];
+            // bins 0..7 again behind bin N-1, so stencils never wrap (bin q1 + A*q2 < 8 <=> q2 == 0 and q1 < 8)
+            if (q1 < 8) buf[N + q1] = v[0];
             bar_arrive(kBarFull + s, kThreads);
-            blk += kHB;
-            row += kHB;
+            blk += HB;
+            row += HB;
             if (row >= p.ring_blocks) row -= p.ring_blocks;
         }
     } else {
@@ -209,7 +254,7 @@ __global__ void __maxnreg__(104)
             have[k] = ch < p.n_channels;
             const float4* kc = reinterpret_cast<const float4*>(c.consts + (have[k] ? ch : 0));
             const float4 k0 = __ldg(kc), k1 = __ldg(kc + 1), k2 = __ldg(kc + 2), k3 = __ldg(kc + 3);
-            off[k] = ((uint32_t)__float_as_int(k0.x) & (uint32_t)(kN - 1)) * 8u;
+            off[k] = ((uint32_t)__float_as_int(k0.x) & (uint32_t)(N - 1)) * 8u;
             sgn[k] = k0.y;
             rot[k] = make_float2(k0.z, k0.w);
             wg[k][0] = k1.x, wg[k][1] = k1.y, wg[k][2] = k1.z, wg[k][3] = k1.w;
@@ -218,12 +263,10 @@ __global__ void __maxnreg__(104)
             R[k] = make_float2(0.0f, 0.0f);
             mx[k] = 0.0f;
         }
-        const unsigned char* spec_b = smem;
         uint32_t s = 0;
         for (uint32_t i = s0; i < s1; ++i, s = (s + 1 == (uint32_t)kBufs) ? 0u : s + 1) {
-            const uint32_t bb = p.b0 + i * kHB;
-            const bool anchor = ((i - s0) % kAnchorEvery) == 0;
-            if (anchor) {
+            const uint32_t bb = p.b0 + i * HB;
+            if (((i - s0) % G::kAnchorEvery) == 0) {
                 // R = P_c[bb] * rot_c from the exact table; between anchors R *= phase_inc per hop
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
@@ -233,45 +276,48 @@ __global__ void __maxnreg__(104)
                 }
             }
             bar_sync(kBarFull + s, kThreads);
-            const bool full = bb + kHB <= p.b1 && (bb & 7u) == 0;  // whole batch, 32-byte aligned row segment
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 if (!have[k]) continue;
-                const unsigned char* base = spec_b + (size_t)s * kHB * kHopStride * 8 + off[k];
-                float out[kHB];
+#pragma unroll 1
+                for (int oct = 0; oct < HB / 8; ++oct) {  // eight hops at a time: one 32-byte store per channel
+                    const uint32_t b8 = bb + 8 * oct;
+                    const unsigned char* base = smem + ((size_t)s * HB + 8 * oct) * HOP * 8 + off[k];
+                    float out[8];
 #pragma unroll
-                for (int h = 0; h < kHB; ++h) {
-                    const float4* bins = reinterpret_cast<const float4*>(base + (size_t)h * kHopStride * 8);
-                    float2 acc = make_float2(0.0f, 0.0f);
+                    for (int h = 0; h < 8; ++h) {
+                        const float4* bins = reinterpret_cast<const float4*>(base + (size_t)h * HOP * 8);
+                        float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 two = bins[q];
-                        acc = ffma2(make_float2(two.x, two.y), bc(wg[k][2 * q]), acc);
-                        acc = ffma2(make_float2(two.z, two.w), bc(wg[k][2 * q + 1]), acc);
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 two = bins[q];
+                            acc = ffma2(make_float2(two.x, two.y), bc(wg[k][2 * q]), acc);
+                            acc = ffma2(make_float2(two.z, two.w), bc(wg[k][2 * q + 1]), acc);
+                        }
+                        const float2 r = R[k];
+                        // audio[b] = {+Re, -Im*sign, -Re, +Im*sign}[b & 3] of acc*R; b8 is a multiple of 4
+                        float o;
+                        if ((h & 3) == 0) o = acc.x * r.x - acc.y * r.y;
+                        else if ((h & 3) == 1) o = -(acc.x * r.y + acc.y * r.x) * sgn[k];
+                        else if ((h & 3) == 2) o = -(acc.x * r.x - acc.y * r.y);
+                        else o = (acc.x * r.y + acc.y * r.x) * sgn[k];
+                        out[h] = o;
+                        R[k] = make_float2(r.x * pinc[k].x - r.y * pinc[k].y, r.x * pinc[k].y + r.y * pinc[k].x);
                     }
-                    const float2 r = R[k];
-                    // audio[b] = {+Re, -Im*sign, -Re, +Im*sign}[b & 3] of acc*R; bb is a multiple of 4
-                    float o;
-                    if ((h & 3) == 0) o = acc.x * r.x - acc.y * r.y;
-                    else if ((h & 3) == 1) o = -(acc.x * r.y + acc.y * r.x) * sgn[k];
-                    else if ((h & 3) == 2) o = -(acc.x * r.x - acc.y * r.y);
-                    else o = (acc.x * r.y + acc.y * r.x) * sgn[k];
-                    out[h] = o;
-                    R[k] = make_float2(r.x * pinc[k].x - r.y * pinc[k].y, r.x * pinc[k].y + r.y * pinc[k].x);
-                }
-                float* dst = p.audio + (size_t)(tid + k * kIntThreads) * p.af_stride + bb;
-                if (full) {
-                    stg256(dst, out);
-                    float m = mx[k];
+                    float* dst = p.audio + (size_t)(tid + k * kIntThreads) * p.af_stride + b8;
+                    if (b8 + 8 <= p.b1 && (b8 & 7u) == 0) {  // whole octet, 32-byte aligned row segment
+                        stg256(dst, out);
+                        float m = mx[k];
 #pragma unroll
-                    for (int h = 0; h < kHB; ++h) m = fmaxf(m, fabsf(out[h]));
-                    mx[k] = m;
-                } else {
+                        for (int h = 0; h < 8; ++h) m = fmaxf(m, fabsf(out[h]));
+                        mx[k] = m;
+                    } else {
 #pragma unroll
-                    for (int h4 = 0; h4 < kHB; h4 += 4) {
-                        if (bb + h4 < p.b1) {  // b1 is a multiple of 4
-                            *reinterpret_cast<float4*>(dst + h4) = make_float4(out[h4], out[h4 + 1], out[h4 + 2], out[h4 + 3]);
-                            mx[k] = fmaxf(mx[k], fmaxf(fmaxf(fabsf(out[h4]), fabsf(out[h4 + 1])), fmaxf(fabsf(out[h4 + 2]), fabsf(out[h4 + 3]))));
+                        for (int h4 = 0; h4 < 8; h4 += 4) {
+                            if (b8 + h4 < p.b1) {  // b1 is a multiple of 4
+                                *reinterpret_cast<float4*>(dst + h4) = make_float4(out[h4], out[h4 + 1], out[h4 + 2], out[h4 + 3]);
+                                mx[k] = fmaxf(mx[k], fmaxf(fmaxf(fabsf(out[h4]), fabsf(out[h4 + 1])), fmaxf(fabsf(out[h4 + 2]), fabsf(out[h4 + 3]))));
+                            }
                         }
                     }
                 }
@@ -291,31 +337,42 @@ __global__ void __maxnreg__(104)
 std::mutex g_attr_mu;
 std::set<std::pair<int, const void*>> g_attr_done;
 
-cudaError_t prepare(const void* kern, int* sms) {
+cudaError_t prepare(const void* kern, size_t smem_bytes, int* sms) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     std::lock_guard<std::mutex> lk(g_attr_mu);
     if (g_attr_done.count({dev, kern})) return cudaSuccess;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
     g_attr_done.insert({dev, kern});
     return cudaSuccess;
 }
 
-template <int KC>
+template <int BS, int KC>
 cudaError_t launch_t(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
-    auto kern = demod_chan_kernel<KC>;
+    constexpr int HB = ChanGeo<BS>::kHB;
+    auto kern = demod_chan_kernel<BS, KC>;
     int sms = 0;
-    cudaError_t e = prepare(reinterpret_cast<const void*>(kern), &sms);
+    cudaError_t e = prepare(reinterpret_cast<const void*>(kern), spec_bytes<BS>(), &sms);
     if (e != cudaSuccess) return e;
-    const uint32_t n_batches = (p.b1 - p.b0 + kHB - 1) / kHB;
+    const uint32_t n_batches = (p.b1 - p.b0 + HB - 1) / HB;
     // one CTA per SM, contiguous runs of batches (anchored phase recurrence, sequential IQ reads)
     const uint32_t per_cta = (n_batches + (uint32_t)sms - 1) / (uint32_t)sms;
     const uint32_t grid = (n_batches + per_cta - 1) / per_cta;
-    kern<<<grid, kThreads, kSpecBytes, s>>>(p, c, n_batches, per_cta);
+    kern<<<grid, kThreads, spec_bytes<BS>(), s>>>(p, c, n_batches, per_cta);
     return cudaGetLastError();
+}
+
+template <int BS>
+cudaError_t launch_bs(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
+    switch ((p.n_channels + kIntThreads - 1) / kIntThreads) {
+        case 1: return launch_t<BS, 1>(p, c, s);
+        case 2: return launch_t<BS, 2>(p, c, s);
+        case 3: return launch_t<BS, 3>(p, c, s);
+        default: return launch_t<BS, 4>(p, c, s);
+    }
 }
 
 }  // namespace
@@ -323,15 +380,15 @@ cudaError_t launch_t(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) 
 uint32_t chan_max_channels() { return kChanMaxChannels; }
 
 cudaError_t launch_demod_chan(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
-    if (p.block_size != 16 || c.taps != kChanTaps || p.n_channels == 0 || p.n_channels > kChanMaxChannels ||
-        p.ring_blocks < 64 || (p.b0 & 3u) || (p.b1 & 3u) || (p.af_stride & 7u))
+    if (c.taps != kChanTaps || p.n_channels == 0 || p.n_channels > kChanMaxChannels || p.ring_blocks < 64 ||
+        (p.b0 & 3u) || (p.b1 & 3u) || (p.af_stride & 7u))
         return cudaErrorInvalidValue;
     if (p.b1 <= p.b0) return cudaSuccess;
-    switch ((p.n_channels + kIntThreads - 1) / kIntThreads) {
-        case 1: return launch_t<1>(p, c, s);
-        case 2: return launch_t<2>(p, c, s);
-        case 3: return launch_t<3>(p, c, s);
-        default: return launch_t<4>(p, c, s);
+    switch (p.block_size) {
+        case 16: return launch_bs<16>(p, c, s);
+        case 8: return launch_bs<8>(p, c, s);
+        case 4: return launch_bs<4>(p, c, s);
+        default: return cudaErrorInvalidValue;
     }
 }
 

@@ -92,7 +92,7 @@ inline bool nco_tables(const SsbdGeometry& g, int32_t demod_freq_hz, bool is_usb
 
 // ---- STFT channelizer tables (cwsl_chan.cu). Not reference arithmetic: a type-2 non-uniform FFT of the
 // reference's window (512 taps on a 1024-point grid) with a Kaiser-Bessel interpolation kernel, all in double.
-constexpr uint32_t kChanGrid = 1024;
+inline uint32_t chan_grid(const SsbdGeometry& g) { return 2 * g.filt_order; }  // 1024 / 512 / 256 bins
 
 struct ChanKernel {
     int w;
@@ -113,30 +113,31 @@ struct ChanKernel {
     }
 };
 
-// window[j] = h[j] / psihat((j - 256)/1024): the low-pass taps pre-compensated for the interpolation kernel
+// window[j] = h[j] / psihat((j - L/2)/N): the low-pass taps pre-compensated for the interpolation kernel
 inline std::vector<float> chan_window(const SsbdGeometry& g, int width) {
     const std::vector<float> h = lowpass_taps(g);
     const ChanKernel k(width);
     std::vector<float> w(h.size());
     for (size_t j = 0; j < h.size(); ++j)
-        w[j] = static_cast<float>((double)h[j] / k.psihat(((double)j - h.size() / 2.0) / kChanGrid));
+        w[j] = static_cast<float>((double)h[j] / k.psihat(((double)j - h.size() / 2.0) / chan_grid(g)));
     return w;
 }
 
-// twiddle[q1*32 + j2] = W1024^(j2*q1) * i^q1 (inter-pass twiddle of the 32x32 FFT and the rotation that moves
-// the phase reference of the spectrum to the window centre)
-inline std::vector<std::complex<float>> chan_twiddles() {
-    std::vector<std::complex<float>> t(32 * 32);
-    for (int q1 = 0; q1 < 32; ++q1)
+// twiddle[q1*32 + j2] = W_N^(j2*q1) * i^q1, q1 < N/32 (inter-pass twiddle of the (N/32) x 32 FFT and the rotation
+// that moves the phase reference of the spectrum to the window centre, e^{+2 pi i q (L/2)/N} = i^q)
+inline std::vector<std::complex<float>> chan_twiddles(const SsbdGeometry& g) {
+    const int n = (int)chan_grid(g), a = n / 32;
+    std::vector<std::complex<float>> t((size_t)a * 32);
+    for (int q1 = 0; q1 < a; ++q1)
         for (int j2 = 0; j2 < 32; ++j2) {
-            const double a = -2.0 * kPi * ((j2 * q1) % (int)kChanGrid) / kChanGrid + kPi / 2.0 * (q1 & 3);
-            t[q1 * 32 + j2] = std::complex<float>((float)std::cos(a), (float)std::sin(a));
+            const double ang = -2.0 * kPi * ((j2 * q1) % n) / n + kPi / 2.0 * (q1 & 3);
+            t[(size_t)q1 * 32 + j2] = std::complex<float>((float)std::cos(ang), (float)std::sin(ang));
         }
     return t;
 }
 
 struct ChanChannel {
-    int q0 = 0;                  // first bin of the stencil (may be negative: bins are taken mod 1024)
+    int q0 = 0;                  // first bin of the stencil (may be negative: bins are taken mod N)
     std::vector<float> wgt;      // [taps]
     std::complex<float> rot;     // e^{-i 240 w}
 };
@@ -151,8 +152,9 @@ inline ChanChannel chan_channel(const SsbdGeometry& g, const NcoTables& t, int w
     const double nominal = (double)t.phase_delta * g.block_size;
     theta += 2.0 * kPi * std::round((nominal - theta) / (2.0 * kPi));
     const double omega = theta / g.block_size;
-    double nu = std::fmod(-omega * kChanGrid / (2.0 * kPi), (double)kChanGrid);
-    if (nu < 0) nu += kChanGrid;
+    const double n = chan_grid(g);
+    double nu = std::fmod(-omega * n / (2.0 * kPi), n);
+    if (nu < 0) nu += n;
     ChanChannel c;
     c.q0 = (int)std::ceil(nu - width / 2.0);
     if (c.q0 & 1) c.q0 -= 1;

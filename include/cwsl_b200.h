@@ -39,11 +39,12 @@ extern "C" {
  *        with strict IEEE flags (oracle/_ref).
  * FAST:  same tables and the same float phase recurrence, FMA-contracted mix and FIR
  *        (packed fma.rn.f32x2) -> <= 1 int16 LSB, residual >= 90 dB below signal.
- * STFT:  same tolerance class as FAST, for receivers with many channels: per 16-sample hop ONE 1024-point FFT
- *        of the windowed last 512 IQ samples is shared by every channel of the slot group, and each channel
- *        reads its NCO frequency off that grid (8-tap Kaiser-Bessel interpolation) and applies the reference's
- *        own float phase recurrence. Used at 192 kHz for groups of >= 48 channels (CWSL_STFT_MIN_CHANNELS);
- *        other groups run the FAST kernel. <= 1 int16 LSB, residual <= -120 dB on the benchmark input;
+ * STFT:  same tolerance class as FAST, for receivers with many channels: per output sample (hop of one SSBD block)
+ *        ONE FFT of the windowed last FiltOrder IQ samples on a 2*FiltOrder grid (1024 / 512 / 256 bins at
+ *        192 / 96 / 48 kHz) is shared by every channel of the slot group, and each channel reads its NCO
+ *        frequency off that grid (8-bin Kaiser-Bessel interpolation) and applies the reference's own float
+ *        phase recurrence. Used for groups of >= 48 channels (CWSL_STFT_MIN_CHANNELS); smaller groups run the
+ *        FAST kernel. <= 1 int16 LSB, residual <= -120 dB on the benchmark input;
  *        dynamic range between channels is that of a float32 FFT (~ -140 dB of the strongest signal). */
 #define CWSL_MODE_EXACT 0
 #define CWSL_MODE_FAST 1
@@ -70,13 +71,14 @@ int cwsl_ssbd_params(uint32_t sample_rate, uint32_t out[9]);
 int cwsl_build_tables(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, float* filter,
                       float* tone, float* phase_inc);
 
-/* Host-side constants of CWSL_MODE_STFT, for tests and diagnostics (no device needed; 192 kHz receivers only).
- * window[512]      low-pass taps divided by the transform of the interpolation kernel;
- * twiddle[2*1024]  (re,im) of W1024^(j2*q1) * i^q1 at [q1*32 + j2], the inter-pass factors of the 32x32 FFT;
+/* Host-side constants of CWSL_MODE_STFT, for tests and diagnostics (no device needed). L = FiltOrder, N = 2 L.
+ * window[L]        low-pass taps divided by the transform of the interpolation kernel;
+ * twiddle[2*N]     (re,im) of W_N^(j2*q1) * i^q1 at [q1*32 + j2], q1 < N/32: the inter-pass factors of the
+ *                  (N/32) x 32 FFT;
  * per channel: q0 = first (even) grid bin of the 8-bin stencil, wgt[8] its real interpolation weights,
- * rot[2] = e^{-i 240 w}, w = the channel's NCO step per input sample. Any output pointer may be NULL.
- * audio[b] = Weaver select of  phase[b] * rot * sum_i wgt[i] * X_b[(q0+i) mod 1024],  X_b[q] = i^q * FFT1024 of
- * (window * the last 512 IQ samples up to and including SSBD block b). */
+ * rot[2] = e^{-i (L/2 - BlockSize) w}, w = the channel's NCO step per input sample. Any output pointer may be NULL.
+ * audio[b] = Weaver select of  phase[b] * rot * sum_i wgt[i] * X_b[(q0+i) mod N],  X_b[q] = i^q * N-point FFT of
+ * (window * the last L IQ samples up to and including SSBD block b). */
 int cwsl_stft_tables(uint32_t sample_rate, float* window, float* twiddle);
 int cwsl_stft_channel(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, int32_t* q0, float* wgt,
                       float* rot);

@@ -61,7 +61,7 @@ def test_channelizer_kernel_shape(cw):
     (<= 104 x 512 threads) that one CTA of the quantise kernel fits beside it on every SM."""
     funcs = _sass(cw)
     chan = {k: v for k, v in funcs.items() if "demod_chan_kernel" in k}
-    assert len(chan) == 4                               # 1..4 channels per interpolation thread
+    assert len(chan) == 12                              # 3 receiver rates x 1..4 channels per interpolation thread
     for name, body in chan.items():
         ops = _ops(body)
         assert ops.count("FADD2") > 100 and ops.count("FFMA2") >= 8

@@ -8,32 +8,39 @@ import pytest
 from cwsl_digi_b200 import synth
 from oracle.oracle import af_size
 
-FS, IQ_LEN, N, L, HOP = 192000, 2048, 1024, 512, 16
+FS, IQ_LEN = 192000, 2048
 
 
-def fft1024_32x32(u, tw):
-    """X[q1 + 32 q2] of the zero-padded window, the way the kernel computes it (two 32-point passes + twiddles);
-    includes the i^q centring rotation that the twiddle table carries."""
-    nb = u.shape[0]
-    up = np.zeros((nb, N), np.complex64)
-    up[:, :L] = u
-    a = up.reshape(nb, 32, 32)                       # [j1, j2]
-    p1 = np.fft.fft(a, axis=1).astype(np.complex64)  # over j1 -> [q1, j2]
-    p1 = p1 * tw[None, :, :]                         # W1024^(j2 q1) * i^q1
+def geo(fs):
+    hop = fs // 12000
+    return 2 * 32 * hop, 32 * hop, hop          # grid N, window L, hop (= SSBD block size)
+
+
+def fft_ax32(u, tw, n):
+    """X[q1 + A q2] of the zero-padded window, the way the kernel computes it (an A-point and a 32-point pass with the
+    inter-pass twiddles, A = N/32); includes the i^q centring rotation that the twiddle table carries."""
+    nb, a = u.shape[0], n // 32
+    up = np.zeros((nb, n), np.complex64)
+    up[:, :u.shape[1]] = u
+    x = up.reshape(nb, a, 32)                        # [j1, j2]
+    p1 = np.fft.fft(x, axis=1).astype(np.complex64)  # over j1 -> [q1, j2]
+    p1 = p1 * tw[None, :, :]                         # W_N^(j2 q1) * i^q1
     p2 = np.fft.fft(p1, axis=2).astype(np.complex64)  # over j2 -> [q1, q2]
-    return np.transpose(p2, (0, 2, 1)).reshape(nb, N)  # bin q1 + 32 q2
+    return np.transpose(p2, (0, 2, 1)).reshape(nb, n)  # bin q1 + A q2
 
 
-def stft_slot(cw, port, iq, freq, usb=True):
+def stft_slot(cw, port, iq, freq, usb=True, fs=FS):
+    N, L, HOP = geo(fs)
     x = (iq[0::2] + 1j * iq[1::2]).astype(np.complex64)
     nb = x.size // HOP
-    t = cw.stft_tables(FS)
+    t = cw.stft_tables(fs)
+    assert t["grid"] == N and t["window"].size == L
     xpad = np.concatenate([np.zeros(L - HOP, np.complex64), x])
     frames = np.lib.stride_tricks.sliding_window_view(xpad, L)[::HOP][:nb]
-    spec = fft1024_32x32(frames * t["window"][None, :], t["twiddle"])
-    c = cw.stft_channel(FS, freq, usb)
+    spec = fft_ax32(frames * t["window"][None, :], t["twiddle"], N)
+    c = cw.stft_channel(fs, freq, usb)
     acc = (spec[:, (c["q0"] + np.arange(8)) % N] * c["wgt"][None, :]).sum(axis=1)
-    tb = port.tables(FS, freq, is_usb=usb)
+    tb = port.tables(fs, freq, is_usb=usb)
     ph = port.phase_table(tb["phase_inc"], nb)
     y = acc * ((ph[:, 0] + 1j * ph[:, 1]) * c["rot"])
     sign = 1.0 if usb else -1.0
@@ -47,16 +54,18 @@ def resid_db(got, want):
     return 20 * np.log10(max(np.sqrt(np.mean(err ** 2)), 1e-300) / np.sqrt(np.mean(want ** 2)))
 
 
-def test_twiddles_are_the_32x32_factors(cw):
-    tw = cw.stft_tables(FS)["twiddle"]
-    q1, j2 = np.meshgrid(np.arange(32), np.arange(32), indexing="ij")
+@pytest.mark.parametrize("fs", [192000, 96000, 48000])
+def test_twiddles_are_the_ax32_factors(cw, fs):
+    N, L, _ = geo(fs)
+    tw = cw.stft_tables(fs)["twiddle"]
+    q1, j2 = np.meshgrid(np.arange(N // 32), np.arange(32), indexing="ij")
     want = np.exp(-2j * np.pi * (q1 * j2) / N) * (1j ** (q1 % 4))
     assert np.abs(tw - want).max() < 1e-6
     # and the decomposition equals a plain zero-padded FFT with the centring rotation
     rng = np.random.default_rng(3)
     u = (rng.standard_normal((4, L)) + 1j * rng.standard_normal((4, L))).astype(np.complex64)
     ref = np.fft.fft(u, n=N, axis=1) * (1j ** (np.arange(N) % 4))
-    assert np.abs(fft1024_32x32(u, tw) - ref).max() < 1e-3
+    assert np.abs(fft_ax32(u, tw, N) - ref).max() < 1e-3
 
 
 def test_stencil_properties(cw):
@@ -69,7 +78,7 @@ def test_stencil_properties(cw):
     with pytest.raises(Exception):
         cw.stft_channel(FS, 90001)            # SSBD.hpp:102 "Signal outside of band (high)"
     with pytest.raises(Exception):
-        cw.stft_channel(96000, 0)             # built for 192 kHz receivers
+        cw.stft_channel(24000, 0)             # Fs/B must be an even integer >= 4 (SSBD.hpp:54)
 
 
 @pytest.mark.parametrize("freq,usb", [(-96000, True), (-26000, True), (37, True), (89636, True), (26000, False)])
@@ -80,6 +89,19 @@ def test_stft_math_matches_the_oracle(cw, port, freq, usb):
     o = port.slot(FS, freq, iq, IQ_LEN, 0.9, af_size(15), is_usb=usb)
     wi = o["write_index"]
     got = stft_slot(cw, port, iq, freq, usb)[:wi]
+    assert resid_db(got, o["raw"][:wi]) <= -110.0
+    q = np.trunc(got * np.float32(o["factor"]) + np.float32(0.5)).astype(np.int32)
+    assert np.abs(q - o["i16"][:wi].astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("fs,freq", [(96000, -48000), (96000, 12345), (96000, 42000), (48000, -24000), (48000, 1500),
+                                     (48000, 18000)])
+def test_stft_math_at_the_other_receiver_rates(cw, port, fs, freq):
+    n = 40 * 1024
+    iq = synth.receiver_iq(n, fs, [freq], receiver=4, tones_per_channel=3)
+    o = port.slot(fs, freq, iq, 1024, 0.9, af_size(15))
+    wi = o["write_index"]
+    got = stft_slot(cw, port, iq, freq, True, fs)[:wi]
     assert resid_db(got, o["raw"][:wi]) <= -110.0
     q = np.trunc(got * np.float32(o["factor"]) + np.float32(0.5)).astype(np.int32)
     assert np.abs(q - o["i16"][:wi].astype(np.int32)).max() <= 1
