@@ -22,4 +22,16 @@ for mode in (cw.MODE_FAST, cw.MODE_EXACT, cw.MODE_STFT):
             rx.push_iq(iq[b * IQ_LEN * 2:(b + 7) * IQ_LEN * 2])
         out, wi = rx.end_slot_numpy(g)
         print("mode", mode, "wi", wi, "checksum", int(out.astype(np.int64).sum()))
+# the channelizer's other geometries (two / four hops per FFT warp): 96 and 48 kHz receivers
+for fs, il in ((96000, 1024), (48000, 512)):
+    fr = [int(f) for f in np.linspace(-fs // 2, fs // 2 - 6000, 20)]
+    x = synth.receiver_iq(70 * il, fs, fr[:2], receiver=1, tones_per_channel=1)
+    with cw.Receiver(0, fs, il, ring_seconds=0.3, mode=cw.MODE_STFT) as rx:
+        g = rx.add_group(15.0)
+        for f in fr:
+            rx.add_channel(g, f, 0.9)
+        for b in range(0, 70, 7):
+            rx.push_iq(x[b * il * 2:(b + 7) * il * 2])
+        out, wi = rx.end_slot_numpy(g)
+        print("stft fs", fs, "wi", wi, "checksum", int(out.astype(np.int64).sum()))
 print("done")
