@@ -12,7 +12,8 @@ import cwsl_digi_b200 as cw
 from cwsl_digi_b200 import synth
 from oracle.oracle import Ref, af_size
 
-FS, IQ_LEN = 192000, 2048
+FS = int(os.environ.get("PROBE_FS", "192000"))
+IQ_LEN = 2048 * FS // 192000
 if os.environ.get("PROBE_PARITY", "1") == "1":
     ref = Ref()
     n = int(2 * FS) // IQ_LEN * IQ_LEN
@@ -38,7 +39,7 @@ if os.environ.get("PROBE_PARITY", "1") == "1":
     rx.close()
 
 for C_ in [int(v) for v in os.environ.get("PROBE_CHANNELS", "64,256,1024,4096").split(",")]:
-    freqs = synth.stress_demod_freqs(C_)
+    freqs = np.rint(np.linspace(-FS // 2, FS // 2 - 6000, C_)).astype(np.int64) if FS != 192000 else synth.stress_demod_freqs(C_)
     nblk = 15 * FS // IQ_LEN
     x = (torch.randn(nblk * IQ_LEN * 2, device="cuda") * 300).contiguous()
     for mode, name in ((cw.MODE_FAST, "fast"), (cw.MODE_STFT, "stft")):
