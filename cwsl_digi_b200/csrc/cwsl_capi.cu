@@ -432,7 +432,8 @@ int process_group(cwsl_rx* rx, Group& g) {
         else
             CK(cwsl::launch_demod_exact(p, rx->stream));
     }
-    else if (rx->mode == CWSL_MODE_STFT && p.n_channels >= stft_min_channels()) {
+    else if (rx->mode == CWSL_MODE_STFT && p.n_channels >= stft_min_channels() && p.ring_blocks >= 64) {
+        // (IQ buffers shorter than two windows stay with the direct kernel)
         // big channel groups: one FFT per hop shared by all channels, <= kChanMaxChannels channels per launch
         for (uint32_t c0 = 0; c0 < p.n_channels; c0 += cwsl::kChanMaxChannels) {
             cwsl::DemodLaunch q = p;
