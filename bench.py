@@ -401,6 +401,9 @@ def run_b200(a):
                    d2h_note="int16 result [1024][240000] per receiver; only the 179968 demodulated columns cross PCIe, "
                             "the zero tail of the managed (cwsl_host_alloc) buffer is already zero on the host",
                    ms_per_step=1e3 * wall / a.steps,
+                   d2h_gbs_per_gpu=len(my_rx) * a.channels * (n_iq // 16) * 2 * a.steps / wall / 1e9,
+                   bound="PCIe: the int16 hand-off alone moves d2h_gbs_per_gpu over this GPU's Gen5 x16 link (~55 GB/s "
+                         "measured for plain pinned copies, tools/numa_probe.py); the kernels need 1/8 of that time",
                    note="pinned host IQ -> cwsl_rx_push_iq -> cwsl_rx_end_slot(host int16); timed region includes "
                         "every H2D and D2H copy; wall clock around a device synchronize, max over ranks; "
                         f"{NBUF} pinned hand-off buffers in rotation")
