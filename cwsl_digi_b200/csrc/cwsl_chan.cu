@@ -9,23 +9,27 @@
 //     y_c[b] = P_c[b] * e^{-i 496 w_c} * W_b(w_c),     W_b(w) = sum_j x[16(b-31)+j] h[j] e^{i w j},   w_c = Theta_c/16
 // and W_b is the DTFT of ONE windowed segment that all channels of the receiver share. The kernel computes it
 // once per hop on a 1024-point grid (zero-padded FFT, oversampling 2) and every channel reads its own frequency
-// off that grid with a W-tap Kaiser-Bessel interpolation (the type-2 non-uniform FFT: the window is pre-divided
+// off that grid with an 8-bin Kaiser-Bessel interpolation (the type-2 non-uniform FFT: the window is pre-divided
 // by the kernel's transform). P_c[b] is still the reference's own drifting float phase recurrence (phase table),
 // so the NCO drift (|P| = 1.0004 after one FT8 slot) is reproduced; only the *within-window* deviation from a pure
 // exponential is dropped. Measured against the reference chain (tools/chan_proto.py, tests): residual <= -120 dB
-// with W = 7/8, <= 1 int16 LSB. Per channel-sample this costs ~1.5 FMA-pipe instructions instead of 24 (folded
+// with a kernel of width 7, <= 1 int16 LSB. Per channel-sample this costs ~1.5 FMA-pipe instructions instead of 24 (folded
 // direct form), which moves the path from the FP32 pipe to shared-memory/HBM bandwidth.
 //
-// One CTA = HB consecutive hops x all channels of the launch. Per batch:
-//   1. stage the (HB+31)*16 IQ samples of the batch into shared memory (zero history before the slot start,
-//      source/Instance.cpp:251),
-//   2. one warp per hop: 1024-point FFT as 32 x 32 (two register-resident radix-2 DIF 32-point passes, one
-//      shared-memory transpose, in place in the hop's spectrum buffer); window, inter-pass twiddles and the
-//      centring rotation i^q come from small L1-resident tables,
-//   3. every thread walks channels: W-tap real-weight interpolation of the complex bins (FFMA2), times
-//      rot_c * P_c[b], Weaver select (source/SSBD.hpp:132-135), max|x|, float4 audio stores.
-// CTAs stride over the batches of the launch and keep per-channel max|x| in shared memory (one atomicMax per
-// channel per CTA at the end).
+// (Written for 192 kHz: window 512, hop 16, grid 1024. At 96 / 48 kHz the window is 256 / 128 taps, the hop 8 / 4
+// samples and the grid 512 / 256 bins; see ChanGeo.)
+//
+// Kernel: persistent and warp-specialised, one 512-thread CTA per SM owning a contiguous run of batches of hops.
+//   warps 0-7  (producers) transform the hops of a batch: the windowed samples straight from the IQ ring (zero
+//              history before the slot start, source/Instance.cpp:251), N-point FFT as (N/32) x 32 -- two
+//              register-resident radix-2 DIF passes with one transpose through the hop's own spectrum buffer --
+//              window, inter-pass twiddles and the centring rotation i^q from small L1-resident tables;
+//   warps 8-15 (consumers) own up to 4 channels per thread for the whole launch (stencil offset, 8 weights, rot*P and
+//              phase_inc in registers): per hop 4 x LDS.128 + 8 x FFMA2, Weaver select (source/SSBD.hpp:132-135),
+//              R <- R * phase_inc with R re-read from the exact phase table every 128 hops, one 32-byte store per
+//              channel and 8 hops, max|x| in a register until the end (one atomicMax per channel and CTA);
+//   spectra are handed over through a ring of three shared-memory buffers with named barriers (bar.arrive /
+//   bar.sync), so the FFT warps run up to two batches ahead of the interpolation warps.
 #include "cwsl_kernels.hpp"
 #include "cwsl_ptx.cuh"
 
