@@ -43,7 +43,7 @@ extern "C" {
  *        ONE FFT of the windowed last FiltOrder IQ samples on a 2*FiltOrder grid (1024 / 512 / 256 bins at
  *        192 / 96 / 48 kHz) is shared by every channel of the slot group, and each channel reads its NCO
  *        frequency off that grid (8-bin Kaiser-Bessel interpolation) and applies the reference's own float
- *        phase recurrence. Used for groups of >= 48 channels (CWSL_STFT_MIN_CHANNELS); smaller groups run the
+ *        phase recurrence. Used for groups of >= 64 channels (CWSL_STFT_MIN_CHANNELS; the measured break-even with the FAST kernel); smaller groups run the
  *        FAST kernel. <= 1 int16 LSB, residual <= -120 dB on the benchmark input;
  *        dynamic range between channels is that of a float32 FFT (~ -140 dB of the strongest signal). */
 #define CWSL_MODE_EXACT 0
