@@ -530,6 +530,40 @@ def test_stft_more_channels_than_one_launch(stress_run):
     assert d[1024:].max() <= 2 * FAST_MAX_LSB and np.abs(outs[cw.MODE_STFT][1024:]).max() > 20000
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_stft_random_channel_sets(gpu, ref, seed):
+    """Random receivers: rate, IQ block length, slot length, channel count, frequencies anywhere in the legal band,
+    mixed sidebands and scale factors, IQ pushed in random chunks. STFT within the FAST bars of the reference chain on
+    two spot channels and within 2 LSB of the FAST kernel on every channel."""
+    cw = gpu
+    rng = np.random.default_rng(1000 + seed)
+    fs = int(rng.choice([192000, 192000, 96000, 48000]))
+    iq_len = int(rng.choice([256, 512, 1024, 2048]))
+    nblk = int(rng.integers(40, 120)) * 2048 // iq_len
+    n_ch = int(rng.integers(3, 90))
+    usb = bool(rng.integers(0, 2))                       # one sideband per receiver in the C API's add_channel default
+    lo_f, hi_f = (-fs // 2, fs // 2 - 6000) if usb else (-fs // 2 + 6000, fs // 2)
+    freqs = [int(f) for f in rng.integers(lo_f, hi_f + 1, n_ch)]
+    scales = [float(s) for s in rng.choice([0.9, 0.2], n_ch)]
+    sig = [f + (1500 if usb else -1500) for f in freqs[:6]]
+    iq = synth.receiver_iq(nblk * iq_len, fs, sig, receiver=seed, tones_per_channel=1)
+    chunks = list(rng.integers(1, 30, 400))
+    res = {}
+    for mode in (cw.MODE_FAST, cw.MODE_STFT):
+        out, raw, wi, stats = run_slot(cw, fs, iq_len, 15.0, list(zip(freqs, scales)), iq, mode, ring_seconds=0.5,
+                                       chunks=chunks, usb=usb)
+        res[mode] = (out, raw, wi, stats)
+    out, raw, wi, stats = res[cw.MODE_STFT]
+    assert wi == res[cw.MODE_FAST][2]
+    d = np.abs(out.astype(np.int32) - res[cw.MODE_FAST][0].astype(np.int32))
+    assert d.max() <= 2 * FAST_MAX_LSB, (fs, iq_len, n_ch, int(d.max()))
+    for c in (0, n_ch - 1):
+        o = ref.slot(fs, freqs[c], iq, iq_len, scales[c], af_size(15), is_usb=usb)
+        assert np.abs(out[c].astype(np.int32) - o["i16"].astype(np.int32)).max() <= FAST_MAX_LSB
+    r = resid_db(raw[0][:wi], ref.slot(fs, freqs[0], iq, iq_len, scales[0], af_size(15), is_usb=usb)["raw"][:wi])
+    assert r <= -FAST_MIN_RESID_DB, r          # channel 0 holds a tone
+
+
 def test_stress_exact_spot_channels(stress_run, ref):
     s = stress_run
     cw, freqs, x, nblk, fs, iq_len = s["cw"], s["freqs"], s["x"], s["nblk"], s["fs"], s["iq_len"]
