@@ -255,8 +255,9 @@ def run_b200(a):
     # The compute stream is a HIGH-priority stream: the receivers' post streams (quantise, D2H) are created with the
     # lowest priority by the library, so a demodulation that becomes runnable together with the previous receiver's
     # quantise pass gets its CTAs placed first and the quantise CTAs fill the rest of each SM.
+    prio = 0 if os.environ.get("CWSL_STREAM_PRIORITIES") == "0" else -1
     try:
-        stream = torch.cuda.Stream(priority=-1)
+        stream = torch.cuda.Stream(priority=prio)
     except Exception:  # noqa: BLE001
         stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -364,7 +365,7 @@ def run_b200(a):
         # not all together), the H2D of the next receiver's IQ rides the same stream, and every finished slot is
         # copied back on its receiver's private copy stream (inside cwsl_rx_end_slot), overlapping the next kernels.
         try:
-            e2e_stream = torch.cuda.Stream(priority=-1)
+            e2e_stream = torch.cuda.Stream(priority=prio)
         except Exception:  # noqa: BLE001
             e2e_stream = torch.cuda.Stream()
         for rx in rxs:

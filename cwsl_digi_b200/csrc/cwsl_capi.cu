@@ -645,6 +645,7 @@ cwsl_rx_t* cwsl_rx_create(int device, uint32_t sample_rate, uint32_t iq_len, dou
     // HBM-bound quantise CTAs fill what is left of every SM, instead of the demodulator waiting for them to drain.
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (const char* e = std::getenv("CWSL_STREAM_PRIORITIES"); e && e[0] == '0') prio_least = prio_greatest = 0;  // diagnostics
     if (cudaStreamCreateWithPriority(&rx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaStreamCreateWithPriority(&rx->copy_stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaEventCreateWithFlags(&rx->ev_out_ready, cudaEventDisableTiming) != cudaSuccess ||
