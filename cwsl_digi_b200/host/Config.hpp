@@ -34,6 +34,10 @@ struct FrontEndConfig {
     float ftAudioScaleFactor = 0.90f;    // wsjtx.ftaudioscalefactor
     float wsprAudioScaleFactor = 0.20f;  // wsjtx.wspraudioscalefactor
     std::string operatorCallsign;        // operator.callsign
+    // Extension (not in the reference's config.ini; unknown to it, ignored there): [gpu] arithmetic=exact|fast|stft,
+    // device=N. Values are the CWSL_MODE_* codes of include/cwsl_b200.h.
+    int kernelMode = 1;                  // gpu.arithmetic, default fast
+    int cudaDevice = 0;                  // gpu.device
 };
 
 // Parse one decoder= value. Throws std::invalid_argument with the reference's message prefix.
@@ -90,6 +94,13 @@ inline FrontEndConfig loadFrontEndConfig(std::istream& in) {
         else if (key == "operator.callsign") cfg.operatorCallsign = val;
         else if (key == "wsjtx.ftaudioscalefactor") cfg.ftAudioScaleFactor = std::stof(val);
         else if (key == "wsjtx.wspraudioscalefactor") cfg.wsprAudioScaleFactor = std::stof(val);
+        else if (key == "gpu.device") cfg.cudaDevice = std::stoi(val);
+        else if (key == "gpu.arithmetic") {
+            if (val == "exact") cfg.kernelMode = 0;
+            else if (val == "fast") cfg.kernelMode = 1;
+            else if (val == "stft") cfg.kernelMode = 2;
+            else throw std::invalid_argument("gpu.arithmetic must be exact, fast or stft");
+        }
     }
     if (cfg.ftAudioScaleFactor > 1.0f || cfg.ftAudioScaleFactor <= 0.0f)  // source/CWSL_DIGI.cpp:952-964
         throw std::invalid_argument("ftaudioscalefactor must be > 0 and <= 1");

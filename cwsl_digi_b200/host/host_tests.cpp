@@ -59,6 +59,12 @@ int main(int argc, char** argv) {
         EXPECT(c.decoders[0].getReporterCallsign() == "N0CALL");
         std::istringstream bad("[decoders]\ndecoder=14074000 FT8\n[wsjtx]\nftaudioscalefactor=1.5\n");
         EXPECT(throws([&] { loadFrontEndConfig(bad); }));
+        EXPECT(c.kernelMode == CWSL_MODE_FAST && c.cudaDevice == 0);
+        std::istringstream gpu("[decoders]\ndecoder=14074000 FT8\n[gpu]\narithmetic=stft\ndevice=3\n");
+        FrontEndConfig cg = loadFrontEndConfig(gpu);
+        EXPECT(cg.kernelMode == CWSL_MODE_STFT && cg.cudaDevice == 3);
+        std::istringstream gbad("[decoders]\ndecoder=14074000 FT8\n[gpu]\narithmetic=double\n");
+        EXPECT(throws([&] { loadFrontEndConfig(gbad); }));
         std::istringstream none("[radio]\nfreqcalibration=1.0\n");
         EXPECT(throws([&] { loadFrontEndConfig(none); }));
     }

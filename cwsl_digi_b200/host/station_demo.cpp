@@ -44,8 +44,9 @@ int main(int argc, char** argv) {
         return 2;
     }
     const int slots = argc > 3 ? std::atoi(argv[3]) : 2;
-    const std::string modeArg = argc > 4 ? argv[4] : "fast";
-    const int mode = modeArg == "exact" ? CWSL_MODE_EXACT : modeArg == "stft" ? CWSL_MODE_STFT : CWSL_MODE_FAST;
+    const std::string modeArg = argc > 4 ? argv[4] : "";   // overrides [gpu] arithmetic= of the config file
+    int mode = -1;
+    if (!modeArg.empty()) mode = modeArg == "exact" ? CWSL_MODE_EXACT : modeArg == "stft" ? CWSL_MODE_STFT : CWSL_MODE_FAST;
     auto printer = std::make_shared<ScreenPrinter>(LOG_LEVEL::INFO);
     FrontEndConfig cfg;
     try {
@@ -54,6 +55,7 @@ int main(int argc, char** argv) {
         printer->err(e.what());
         return EXIT_FAILURE;
     }
+    if (mode < 0) mode = cfg.kernelMode;
     printer->print("Found " + std::to_string(cfg.decoders.size()) + " decoder entries");
     if (cwsl_device_count() <= 0) {
         printer->err("no CUDA device: the B200 front-end has no CPU path");
