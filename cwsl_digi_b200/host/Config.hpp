@@ -34,8 +34,8 @@ struct FrontEndConfig {
     float ftAudioScaleFactor = 0.90f;    // wsjtx.ftaudioscalefactor
     float wsprAudioScaleFactor = 0.20f;  // wsjtx.wspraudioscalefactor
     std::string operatorCallsign;        // operator.callsign
-    // Extension (not in the reference's config.ini; unknown to it, ignored there): [gpu] arithmetic=exact|fast|stft,
-    // device=N. Values are the CWSL_MODE_* codes of include/cwsl_b200.h.
+    // Extension (not in the reference's config.ini; the reference parses with allow_unregistered = true,
+    // source/CWSL_DIGI.cpp:607, so it skips them): [gpu] arithmetic=exact|fast|stft, device=N. Values are the CWSL_MODE_* codes of include/cwsl_b200.h.
     int kernelMode = 1;                  // gpu.arithmetic, default fast
     int cudaDevice = 0;                  // gpu.device
 };
