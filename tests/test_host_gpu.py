@@ -12,11 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "cwsl_digi_b200", "host")
 
 
-def test_station_demo_writes_reference_format_wavs(tmp_path, gpu):
+@pytest.mark.parametrize("mode", ["exact", "stft"])   # (stft: the channelizer kernel, forced for small groups by conftest)
+def test_station_demo_writes_reference_format_wavs(tmp_path, gpu, mode):
     exe = os.path.join(HOST, "station_demo")
     if not os.path.exists(exe):
         subprocess.run(["make", "-C", HOST, "all"], check=True, stdout=subprocess.DEVNULL)
-    r = subprocess.run([exe, os.path.join(ROOT, "tests", "data", "station_20m.ini"), str(tmp_path), "1", "exact"],
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "data", "station_20m.ini"), str(tmp_path), "1", mode],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     wavs = sorted(p for p in os.listdir(tmp_path) if p.endswith(".wav"))
