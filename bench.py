@@ -5,15 +5,21 @@ Workload (BASELINE.json configs[4], the configuration the metric's per-GPU targe
   64 synthetic 192 kHz receivers x 1024 decoder channels each, one 15 s FT8 slot per step,
   demodFreq_c = -96000 + round(c*186000/1023); receivers are partitioned round-robin over the
   ranks (one process per GPU, no data-path collective) -> "scaling": "strong".
-A step = every receiver of the rank: NCO mix + 512-tap FIR + /16 + SSB demod for all 1024 channels
-(one launch), max|x| -> normalise -> int16 for all channels (one launch), max reset (one launch).
+A step = every receiver of the rank: demodulation of all 1024 channels (one launch: NCO mix + 512-tap FIR + /16 +
+SSB demod), max|x| -> normalise -> int16 for all channels (one launch), max reset (one launch).
+--mode selects the demodulator: stft (default; one FFT per output sample shared by all channels of the receiver +
+per-channel interpolation, <= 1 LSB), fast (direct-form FFMA2 kernel, <= 1 LSB), exact (bit-identical to the
+reference). The line also carries the other two modes' throughput on the same receivers (other_modes) and an in-run
+parity check of fast/stft against exact (parity_in_run).
 
   value   : ch-samples/s with the IQ already resident in HBM (bind_device_iq), all ranks summed
   e2e     : same metric through the C ABI with HOST buffers: pinned IQ -> cwsl_rx_push_iq (H2D) ->
-            cwsl_rx_end_slot (kernels + D2H of the whole [1024][240000] int16 result)
-  roofline: the demodulator kernel against the FP32 FMA pipe (134 flop per
-            channel-sample; the path is FMA-bound, not HBM-bound); peak = FFMA2 microbenchmark run
-            in this process (MEASURED_PEAKS.json has no FP32 figure); HBM fraction given alongside.
+            cwsl_rx_end_slot (kernels + D2H of the [1024][179968] demodulated part of the int16 result); PCIe-bound
+  roofline: stft: the channelizer kernel's algorithmic HBM bytes (IQ once + float audio once) against
+            MEASURED_PEAKS.json hbm_gbs ("bound": "hbm"; its real limiter, shared-memory bandwidth, is named in
+            roofline.limiter). fast / exact: the direct-form kernels against the FP32 FMA pipe (SURVEY.md section 8d:
+            134 flop per channel-sample), peak = FFMA2 microbenchmark run in this process (MEASURED_PEAKS.json has no
+            FP32 figure), HBM fraction given alongside.
   cpu_baseline / --impl reference: the reference's own SSBD.hpp/LowPass.hpp chain (oracle/_ref,
             -O3 -mavx2 -mfma -ffast-math = the shipped /O2 /fp:fast /arch:AVX analogue), one worker
             thread per host core, on a bounded sample of the same workload.
