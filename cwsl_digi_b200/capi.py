@@ -19,6 +19,7 @@ SYMBOLS = [
     "cwsl_rx_process", "cwsl_rx_end_slot", "cwsl_rx_device_audio", "cwsl_rx_copy_device_audio", "cwsl_rx_read_float_audio",
     "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_wait_output", "cwsl_rx_stream", "cwsl_rx_set_stream", "cwsl_rx_enable_timing",
     "cwsl_rx_kernel_times", "cwsl_measure_fp32_peak", "cwsl_host_alloc", "cwsl_host_free",
+    "cwsl_rx_set_stft_guard", "cwsl_rx_remove_channel", "cwsl_rx_kernel_times_ex", "cwsl_rx_guard_stats",
 ]
 
 
@@ -94,6 +95,10 @@ def lib() -> C.CDLL:
     L.cwsl_rx_enable_timing.argtypes = [vp, C.c_int]
     L.cwsl_rx_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int)]
+    L.cwsl_rx_set_stft_guard.argtypes = [vp, C.c_double]
+    L.cwsl_rx_remove_channel.argtypes = [vp, C.c_int, C.c_int]
+    L.cwsl_rx_kernel_times_ex.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.cwsl_rx_guard_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.cwsl_host_alloc.restype = vp
     L.cwsl_host_alloc.argtypes = [sz]
     L.cwsl_host_free.restype = None
@@ -211,6 +216,19 @@ class Receiver:
     def set_mode(self, mode: int):
         _check(self._L.cwsl_rx_set_mode(self._h, mode))
 
+    def set_stft_guard(self, db_below_band_power: float):
+        """Threshold of the STFT mode's dynamic-range guard (dB below the band's mean power); 0 = off."""
+        _check(self._L.cwsl_rx_set_stft_guard(self._h, float(db_below_band_power)))
+
+    def remove_channel(self, group: int, channel: int) -> None:
+        _check(self._L.cwsl_rx_remove_channel(self._h, group, channel))
+
+    def guard_stats(self, group: int) -> dict:
+        """Last finished slot: channel segments the STFT guard decided, and how many it had the FAST kernel redo."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self._L.cwsl_rx_guard_stats(self._h, group, C.byref(a), C.byref(b)))
+        return dict(decided=a.value, redone=b.value)
+
     def enable_timing(self, on: bool = True):
         _check(self._L.cwsl_rx_enable_timing(self._h, int(on)))
 
@@ -294,7 +312,10 @@ class Receiver:
         return self._L.cwsl_rx_stream(self._h)
 
     def kernel_times(self) -> dict:
-        d, q = C.c_float(), C.c_float()
-        nd, nq = C.c_int(), C.c_int()
-        _check(self._L.cwsl_rx_kernel_times(self._h, C.byref(d), C.byref(q), C.byref(nd), C.byref(nq)))
-        return dict(demod_ms=d.value, quant_ms=q.value, demod_launches=nd.value, quant_launches=nq.value)
+        """CUDA-event times since the last call. demod_ms: whole demodulation passes; main_ms: the demodulator
+        kernel(s) alone; guard_pre_ms / guard_post_ms: the STFT guard's band-power pass and its selection + redo."""
+        ms = (C.c_float * 5)()
+        n = (C.c_int * 2)()
+        _check(self._L.cwsl_rx_kernel_times_ex(self._h, ms, n))
+        return dict(demod_ms=ms[0], quant_ms=ms[1], main_ms=ms[2], guard_pre_ms=ms[3], guard_post_ms=ms[4],
+                    demod_launches=n[0], quant_launches=n[1])

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -58,7 +59,7 @@ struct PhaseEntry {
     float2* table = nullptr;
     int refs = 0;
 };
-std::mutex g_mu;
+std::mutex g_mu;  // phase-table / anchor / per-device constant caches
 std::map<PhaseKey, PhaseEntry> g_phase_cache;
 std::set<std::pair<int, uint32_t>> g_taps_uploaded;
 struct ChanDeviceTables {  // STFT channelizer: deconvolved window and FFT twiddles, one copy per device
@@ -66,6 +67,14 @@ struct ChanDeviceTables {  // STFT channelizer: deconvolved window and FFT twidd
     float2* twiddle = nullptr;
 };
 std::map<std::pair<int, uint32_t>, ChanDeviceTables> g_chan_tables;  // per (device, block size)
+// STFT anchor tables P_c[128 a], [anchor][channel]: shared by every slot group with the same channel list
+// (64 receivers of the stress sweep share one 15 MB table instead of holding 1 GB of copies)
+struct AnchorEntry {
+    float2* table = nullptr;
+    uint32_t n_anchor = 0;
+    int refs = 0;
+};
+std::map<std::vector<PhaseKey>, AnchorEntry> g_anchor_cache;
 
 // Managed hand-off buffers (cwsl_host_alloc): pinned, zero-initialised, and only ever written by
 // cwsl_rx_end_slot, so the library knows which columns of a destination can hold non-zero data and
@@ -78,7 +87,8 @@ struct HostRegion {
     size_t bytes = 0;
     std::map<uintptr_t, OutState> outs;
 };
-std::map<uintptr_t, HostRegion> g_host_regions;  // base address -> region (guarded by g_mu)
+std::mutex g_host_mu;  // its own lock: a long table build under g_mu must not stall another receiver's end_slot
+std::map<uintptr_t, HostRegion> g_host_regions;  // base address -> region
 
 struct ChannelHost {
     int32_t demod_freq = 0;
@@ -93,6 +103,9 @@ struct Group {
     size_t af_stride = 0;
     std::vector<ChannelHost> ch;
     std::vector<PhaseKey> phase_keys;
+    // channel-set changes requested while a slot is open: applied at the slot edge (cwsl_rx_end_slot)
+    std::vector<ChannelHost> pending_add;
+    std::vector<int> pending_remove;
     // device
     float2* d_tone = nullptr;
     const float2** d_phase = nullptr;
@@ -103,13 +116,28 @@ struct Group {
     float* d_maxval = nullptr;
     float* d_audio = nullptr;
     int16_t* d_out = nullptr;
-    cwsl::ChanConst* d_chan = nullptr;  // STFT channelizer constants (192 kHz receivers)
+    cwsl::ChanConst* d_chan = nullptr;  // STFT channelizer constants
+    // STFT mode only, allocated at its first use (ensure_stft): anchors of the exact phase recurrence and the
+    // dynamic-range guard's per-launch scratch
+    const float2* d_anchors = nullptr;  // shared, see g_anchor_cache
+    bool have_anchor_ref = false;
+    float* d_seg_scale = nullptr;
+    unsigned* d_seg_max = nullptr;
+    unsigned* d_seg_energy = nullptr;
+    uint32_t* d_sel = nullptr;
+    cwsl::GuardItem* d_items = nullptr;
+    unsigned* d_n_items = nullptr;
+    unsigned long long* d_counters = nullptr;  // [0,1] this slot, [2,3] last finished slot
+    uint32_t max_segs = 0;
+    uint32_t tiles = 1;        // FAST tiles per segment: a function of the group's size only
+    int mode = CWSL_MODE_FAST; // arithmetic mode of the OPEN slot (latched from the receiver at the slot's first launch)
     // slot state (units: SSBD blocks unless noted)
     uint64_t slot_start = 0;   // absolute index of the slot's block 0
     uint64_t processed = 0;    // slot-relative blocks already demodulated
     uint64_t iq_blocks = 0;    // IQ blocks pushed since the slot edge
     size_t last_write_index = 0;
     bool have_result = false;
+    bool committed = false;
 };
 
 }  // namespace
@@ -137,9 +165,14 @@ struct cwsl_rx {
     bool bound = false;
     bool committed = false;
     std::vector<Group> groups;
+    double guard_db = 0;  // STFT dynamic-range guard threshold (dB below the band's mean power); <= 0: off
     // timing
     bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_demod, ev_quant;
+    struct DemodEvents {
+        cudaEvent_t e0 = nullptr, e_pre = nullptr, e_main = nullptr, e1 = nullptr;  // e_pre/e_main: STFT launches only
+    };
+    std::vector<DemodEvents> ev_demod;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_quant;
     std::vector<cudaEvent_t> ev_pool;
 };
 
@@ -168,6 +201,17 @@ cudaEvent_t get_event(cwsl_rx* rx) {
     return e;
 }
 
+void release_anchor_ref(Group& g) {  // g_mu held
+    if (!g.have_anchor_ref) return;
+    auto it = g_anchor_cache.find(g.phase_keys);
+    if (it != g_anchor_cache.end() && --it->second.refs <= 0) {
+        cudaFree(it->second.table);
+        g_anchor_cache.erase(it);
+    }
+    g.have_anchor_ref = false;
+    g.d_anchors = nullptr;
+}
+
 void free_group_device(Group& g) {
     cudaFree(g.d_tone);
     cudaFree((void*)g.d_phase);
@@ -179,13 +223,26 @@ void free_group_device(Group& g) {
     cudaFree(g.d_audio);
     cudaFree(g.d_out);
     cudaFree(g.d_chan);
+    cudaFree(g.d_seg_scale);
+    cudaFree(g.d_seg_max);
+    cudaFree(g.d_seg_energy);
+    cudaFree(g.d_sel);
+    cudaFree(g.d_items);
+    cudaFree(g.d_n_items);
+    cudaFree(g.d_counters);
     g.d_chan = nullptr;
     g.d_tone = nullptr;
     g.d_phase = nullptr;
-    g.d_sign = g.d_scale = g.d_factor = g.d_maxval = g.d_audio = nullptr;
-    g.d_maxbits = nullptr;
+    g.d_sign = g.d_scale = g.d_factor = g.d_maxval = g.d_audio = g.d_seg_scale = nullptr;
+    g.d_maxbits = g.d_seg_max = g.d_seg_energy = g.d_n_items = nullptr;
+    g.d_sel = nullptr;
+    g.d_items = nullptr;
+    g.d_counters = nullptr;
     g.d_out = nullptr;
+    g.max_segs = 0;
+    g.committed = false;
     std::lock_guard<std::mutex> lk(g_mu);
+    release_anchor_ref(g);
     for (const PhaseKey& k : g.phase_keys) {
         auto it = g_phase_cache.find(k);
         if (it != g_phase_cache.end() && --it->second.refs <= 0) {
@@ -196,151 +253,232 @@ void free_group_device(Group& g) {
     g.phase_keys.clear();
 }
 
-int commit_impl(cwsl_rx* rx);
+bool commit_nosync() {
+    static const bool nosync = [] {
+        const char* e = std::getenv("CWSL_COMMIT_NOSYNC");
+        return e && e[0] == '1';
+    }();
+    return nosync;
+}
 
-// Upload tables, build missing phase tables, allocate audio buffers. Idempotent; on failure everything this
+int commit_device_tables(cwsl_rx* rx);
+int commit_group_impl(cwsl_rx* rx, Group& g);
+
+// Upload one slot group's tables, build missing phase tables, allocate its audio buffers. On failure everything this
 // attempt allocated is released again, so a later call starts from scratch instead of leaking.
-int commit(cwsl_rx* rx) {
-    if (rx->committed) return CWSL_OK;
-    const int rc = commit_impl(rx);
+int commit_group(cwsl_rx* rx, Group& g) {
+    if (g.committed) return CWSL_OK;
+    // One-time setup allocates GBs of device memory. Do it on a quiet device: with more than ~8 receivers on private
+    // non-blocking streams, cudaMalloc overlapping other receivers' running kernels ended in "illegal memory access"
+    // on driver 580 / CUDA 12.9 (any kernel, TMA or not; compute-sanitizer clean).
+    // CWSL_COMMIT_NOSYNC=1 disables the synchronisation (diagnostics only).
+    if (!commit_nosync()) CK(cudaDeviceSynchronize());
+    const int rc = commit_group_impl(rx, g);
     if (rc != CWSL_OK) {
         const std::string msg = g_last_error;  // free_group_device must not clobber the reason
-        for (Group& g : rx->groups) free_group_device(g);
+        free_group_device(g);
         g_last_error = msg;
     }
     return rc;
 }
 
-int commit_impl(cwsl_rx* rx) {
+int commit(cwsl_rx* rx) {
+    if (rx->committed) return CWSL_OK;
     if (rx->groups.empty()) return fail(CWSL_ERR_STATE, "no slot group defined");
-    // One-time setup of this receiver allocates GBs of device memory. Do it on a quiet device: with more than
-    // ~8 receivers on private non-blocking streams, cudaMalloc overlapping other receivers' running kernels
-    // ended in "illegal memory access" on driver 580 / CUDA 12.9 (any kernel, TMA or not; compute-sanitizer
-    // clean). CWSL_COMMIT_NOSYNC=1 disables the synchronisation (diagnostics only).
-    static const bool nosync = [] {
-        const char* e = std::getenv("CWSL_COMMIT_NOSYNC");
-        return e && e[0] == '1';
-    }();
-    if (!nosync) CK(cudaDeviceSynchronize());
-    // constant-bank taps (once per device and block size), cross-checked against the baked copy
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        const auto key = std::make_pair(rx->device, rx->geo.block_size);
-        if (!g_taps_uploaded.count(key)) {
-            const std::vector<float> h = cwsl::lowpass_taps(rx->geo);
-            const float* baked = cwsl::baked_taps_transposed(rx->geo.block_size);
-            if (!baked) return fail(CWSL_ERR_INVALID, "unsupported block size %u", rx->geo.block_size);
-            for (uint32_t m = 0; m < rx->geo.block_size; ++m)
-                for (uint32_t n = 0; n < 32; ++n)
-                    if (std::memcmp(&baked[m * 32 + n], &h[rx->geo.block_size * n + m], sizeof(float)) != 0)
-                        return fail(CWSL_ERR_STATE,
-                                    "baked low-pass taps differ from this host's libm result at tap %u "
-                                    "(rebuild: make -C cwsl_digi_b200/csrc taps all)",
-                                    rx->geo.block_size * n + m);
-            CK(cwsl::upload_taps(rx->geo.block_size, h.data()));
-            g_taps_uploaded.insert(key);
-        }
-        if (!g_chan_tables.count(key)) {  // STFT window + FFT twiddles, once per device and rate
-            const std::vector<float> w = cwsl::chan_window(rx->geo, cwsl::kChanKernelWidth);
-            const std::vector<std::complex<float>> tw = cwsl::chan_twiddles(rx->geo);
-            ChanDeviceTables t;
-            CK(cudaMalloc(&t.window, w.size() * sizeof(float)));
-            CK(cudaMalloc(&t.twiddle, tw.size() * sizeof(float2)));
-            CK(cudaMemcpy(t.window, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(t.twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-            g_chan_tables[key] = t;
-        }
-        rx->chan_tables = g_chan_tables[key];
-    }
+    int rc = commit_device_tables(rx);
+    if (rc != CWSL_OK) return rc;
     uint64_t max_blocks = 0;
     for (Group& g : rx->groups) {
-        const uint32_t C = (uint32_t)g.ch.size();
-        if (C == 0) return fail(CWSL_ERR_STATE, "slot group without channels");
-        const uint32_t BS = rx->geo.block_size;
-        g.af_stride = (g.af_size + 7) / 8 * 8;
+        if (g.ch.empty()) return fail(CWSL_ERR_STATE, "slot group without channels");
+        if ((rc = commit_group(rx, g)) != CWSL_OK) {
+            const std::string msg = g_last_error;
+            for (Group& h : rx->groups) free_group_device(h);
+            g_last_error = msg;
+            return rc;
+        }
         max_blocks = std::max<uint64_t>(max_blocks, g.af_size);
-        std::vector<float2> tone((size_t)C * BS);
-        std::vector<float> sign(C), scale(C);
-        for (uint32_t c = 0; c < C; ++c) {
-            for (uint32_t m = 0; m < BS; ++m)
-                tone[(size_t)c * BS + m] = make_float2(g.ch[c].nco.tone[m].real(), g.ch[c].nco.tone[m].imag());
-            sign[c] = g.ch[c].nco.sign;
-            scale[c] = g.ch[c].scale;
-        }
-        CK(cudaMalloc(&g.d_tone, tone.size() * sizeof(float2)));
-        CK(cudaMalloc((void**)&g.d_phase, C * sizeof(float2*)));
-        CK(cudaMalloc(&g.d_sign, C * sizeof(float)));
-        CK(cudaMalloc(&g.d_scale, C * sizeof(float)));
-        CK(cudaMalloc(&g.d_maxbits, C * sizeof(unsigned)));
-        CK(cudaMalloc(&g.d_factor, C * sizeof(float)));
-        CK(cudaMalloc(&g.d_maxval, C * sizeof(float)));
-        CK(cudaMalloc(&g.d_audio, (size_t)C * g.af_stride * sizeof(float)));
-        CK(cudaMalloc(&g.d_out, (size_t)C * g.af_size * sizeof(int16_t)));
-        CK(cudaMemcpyAsync(g.d_tone, tone.data(), tone.size() * sizeof(float2), cudaMemcpyHostToDevice, rx->stream));
-        CK(cudaMemcpyAsync(g.d_sign, sign.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
-        CK(cudaMemcpyAsync(g.d_scale, scale.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
-        CK(cudaMemsetAsync(g.d_maxbits, 0, C * sizeof(unsigned), rx->stream));
-        std::vector<cwsl::ChanConst> cconst;
-        {  // STFT channelizer constants (CWSL_MODE_STFT)
-            cconst.resize(C);
-            for (uint32_t c = 0; c < C; ++c) {
-                const cwsl::ChanChannel cc = cwsl::chan_channel(rx->geo, g.ch[c].nco, cwsl::kChanKernelWidth, cwsl::kChanTaps);
-                cconst[c].q0 = cc.q0;
-                cconst[c].sign = g.ch[c].nco.sign;
-                cconst[c].rot[0] = cc.rot.real();
-                cconst[c].rot[1] = cc.rot.imag();
-                for (int i = 0; i < cwsl::kChanTaps; ++i) cconst[c].wgt[i] = cc.wgt[i];
-                cconst[c].pinc[0] = g.ch[c].nco.phase_inc.real();
-                cconst[c].pinc[1] = g.ch[c].nco.phase_inc.imag();
-                cconst[c].pad[0] = cconst[c].pad[1] = 0.0f;
-            }
-            CK(cudaMalloc(&g.d_chan, C * sizeof(cwsl::ChanConst)));
-            CK(cudaMemcpyAsync(g.d_chan, cconst.data(), C * sizeof(cwsl::ChanConst), cudaMemcpyHostToDevice, rx->stream));
-        }
-        CK(cudaStreamSynchronize(rx->stream));  // host vectors go out of scope
-
-        // phase tables: one per distinct (Fs, demodFreq, sideband, length), shared process-wide
-        const uint32_t length = (uint32_t)((g.af_size + 3) / 4 * 4 + 4);
-        std::vector<const float2*> ptrs(C);
-        {
-            // The cache lock is held until the new tables are BUILT: another thread setting up a receiver with
-            // the same frequencies must never see a table that is allocated but not yet filled.
-            std::lock_guard<std::mutex> lk(g_mu);
-            std::vector<float2> new_inc;
-            std::vector<float2*> new_tab;
-            for (uint32_t c = 0; c < C; ++c) {
-                PhaseKey k{rx->device, rx->fs, g.ch[c].demod_freq, g.ch[c].usb, length};
-                PhaseEntry& e = g_phase_cache[k];
-                if (!e.table) {
-                    cudaError_t err = cudaMalloc(&e.table, (size_t)length * sizeof(float2));
-                    if (err != cudaSuccess) {
-                        g_phase_cache.erase(k);
-                        return fail(CWSL_ERR_NOMEM, "phase table alloc: %s", cudaGetErrorString(err));
-                    }
-                    new_inc.push_back(make_float2(g.ch[c].nco.phase_inc.real(), g.ch[c].nco.phase_inc.imag()));
-                    new_tab.push_back(e.table);
-                }
-                ++e.refs;
-                g.phase_keys.push_back(k);
-                ptrs[c] = e.table;
-            }
-            if (!new_tab.empty()) {
-                float2* d_inc = nullptr;
-                float2** d_tab = nullptr;
-                CK(cudaMalloc(&d_inc, new_inc.size() * sizeof(float2)));
-                CK(cudaMalloc((void**)&d_tab, new_tab.size() * sizeof(float2*)));
-                CK(cudaMemcpy(d_inc, new_inc.data(), new_inc.size() * sizeof(float2), cudaMemcpyHostToDevice));
-                CK(cudaMemcpy((void*)d_tab, new_tab.data(), new_tab.size() * sizeof(float2*), cudaMemcpyHostToDevice));
-                CK(cwsl::launch_phase_tables(d_inc, d_tab, (uint32_t)new_tab.size(), length, rx->stream));
-                CK(cudaStreamSynchronize(rx->stream));
-                cudaFree(d_inc);
-                cudaFree((void*)d_tab);
-            }
-        }
-        CK(cudaMemcpy((void*)g.d_phase, ptrs.data(), C * sizeof(float2*), cudaMemcpyHostToDevice));
     }
     rx->max_slot_blocks = max_blocks;
     rx->committed = true;
+    return CWSL_OK;
+}
+
+// constant-bank taps (once per device and block size), cross-checked against the baked copy; STFT window/twiddles
+int commit_device_tables(cwsl_rx* rx) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const auto key = std::make_pair(rx->device, rx->geo.block_size);
+    if (!g_taps_uploaded.count(key)) {
+        const std::vector<float> h = cwsl::lowpass_taps(rx->geo);
+        const float* baked = cwsl::baked_taps_transposed(rx->geo.block_size);
+        if (!baked) return fail(CWSL_ERR_INVALID, "unsupported block size %u", rx->geo.block_size);
+        for (uint32_t m = 0; m < rx->geo.block_size; ++m)
+            for (uint32_t n = 0; n < 32; ++n)
+                if (std::memcmp(&baked[m * 32 + n], &h[rx->geo.block_size * n + m], sizeof(float)) != 0)
+                    return fail(CWSL_ERR_STATE,
+                                "baked low-pass taps differ from this host's libm result at tap %u "
+                                "(rebuild: make -C cwsl_digi_b200/csrc taps all)",
+                                rx->geo.block_size * n + m);
+        CK(cwsl::upload_taps(rx->geo.block_size, h.data()));
+        g_taps_uploaded.insert(key);
+    }
+    if (!g_chan_tables.count(key)) {  // STFT window + FFT twiddles, once per device and rate
+        const std::vector<float> w = cwsl::chan_window(rx->geo, cwsl::kChanKernelWidth);
+        const std::vector<std::complex<float>> tw = cwsl::chan_twiddles(rx->geo);
+        ChanDeviceTables t;
+        CK(cudaMalloc(&t.window, w.size() * sizeof(float)));
+        CK(cudaMalloc(&t.twiddle, tw.size() * sizeof(float2)));
+        CK(cudaMemcpy(t.window, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(t.twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        g_chan_tables[key] = t;
+    }
+    rx->chan_tables = g_chan_tables[key];
+    return CWSL_OK;
+}
+
+int commit_group_impl(cwsl_rx* rx, Group& g) {
+    const uint32_t C = (uint32_t)g.ch.size();
+    if (C == 0) return fail(CWSL_ERR_STATE, "slot group without channels");
+    const uint32_t BS = rx->geo.block_size;
+    g.af_stride = (g.af_size + 7) / 8 * 8;
+    g.tiles = cwsl::fast_tiles_per_seg(C);
+    std::vector<float2> tone((size_t)C * BS);
+    std::vector<float> sign(C), scale(C);
+    for (uint32_t c = 0; c < C; ++c) {
+        for (uint32_t m = 0; m < BS; ++m)
+            tone[(size_t)c * BS + m] = make_float2(g.ch[c].nco.tone[m].real(), g.ch[c].nco.tone[m].imag());
+        sign[c] = g.ch[c].nco.sign;
+        scale[c] = g.ch[c].scale;
+    }
+    CK(cudaMalloc(&g.d_tone, tone.size() * sizeof(float2)));
+    CK(cudaMalloc((void**)&g.d_phase, C * sizeof(float2*)));
+    CK(cudaMalloc(&g.d_sign, C * sizeof(float)));
+    CK(cudaMalloc(&g.d_scale, C * sizeof(float)));
+    CK(cudaMalloc(&g.d_maxbits, C * sizeof(unsigned)));
+    CK(cudaMalloc(&g.d_factor, C * sizeof(float)));
+    CK(cudaMalloc(&g.d_maxval, C * sizeof(float)));
+    CK(cudaMalloc(&g.d_audio, (size_t)C * g.af_stride * sizeof(float)));
+    CK(cudaMalloc(&g.d_out, (size_t)C * g.af_size * sizeof(int16_t)));
+    CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
+    CK(cudaMemcpyAsync(g.d_tone, tone.data(), tone.size() * sizeof(float2), cudaMemcpyHostToDevice, rx->stream));
+    CK(cudaMemcpyAsync(g.d_sign, sign.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
+    CK(cudaMemcpyAsync(g.d_scale, scale.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
+    CK(cudaMemsetAsync(g.d_maxbits, 0, C * sizeof(unsigned), rx->stream));
+    CK(cudaMemsetAsync(g.d_counters, 0, 4 * sizeof(unsigned long long), rx->stream));
+    std::vector<cwsl::ChanConst> cconst(C);
+    for (uint32_t c = 0; c < C; ++c) {  // STFT channelizer constants (CWSL_MODE_STFT)
+        const cwsl::ChanChannel cc = cwsl::chan_channel(rx->geo, g.ch[c].nco, cwsl::kChanKernelWidth, cwsl::kChanTaps);
+        cconst[c].q0 = cc.q0;
+        cconst[c].sign = g.ch[c].nco.sign;
+        cconst[c].rot[0] = cc.rot.real();
+        cconst[c].rot[1] = cc.rot.imag();
+        for (int i = 0; i < cwsl::kChanTaps; ++i) cconst[c].wgt[i] = cc.wgt[i];
+        cconst[c].pinc[0] = g.ch[c].nco.phase_inc.real();
+        cconst[c].pinc[1] = g.ch[c].nco.phase_inc.imag();
+        cconst[c].pad[0] = cconst[c].pad[1] = 0.0f;
+    }
+    CK(cudaMalloc(&g.d_chan, C * sizeof(cwsl::ChanConst)));
+    CK(cudaMemcpyAsync(g.d_chan, cconst.data(), C * sizeof(cwsl::ChanConst), cudaMemcpyHostToDevice, rx->stream));
+    CK(cudaStreamSynchronize(rx->stream));  // host vectors go out of scope
+
+    // phase tables: one per distinct (Fs, demodFreq, sideband, length), shared process-wide. New tables are built
+    // into local pointers and PUBLISHED to the cache only when they are complete: a failed build leaves nothing
+    // half-made behind, and nobody can ever pick up a table that is allocated but not yet filled.
+    const uint32_t length = (uint32_t)((g.af_size + 3) / 4 * 4 + 4);
+    std::vector<const float2*> ptrs(C);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        std::map<PhaseKey, float2*> fresh;
+        std::vector<float2> new_inc;
+        std::vector<float2*> new_tab;
+        auto drop_fresh = [&] {
+            for (auto& kv : fresh) cudaFree(kv.second);
+        };
+        for (uint32_t c = 0; c < C; ++c) {
+            const PhaseKey k{rx->device, rx->fs, g.ch[c].demod_freq, g.ch[c].usb, length};
+            if (g_phase_cache.count(k) || fresh.count(k)) continue;
+            float2* tab = nullptr;
+            const cudaError_t err = cudaMalloc(&tab, (size_t)length * sizeof(float2));
+            if (err != cudaSuccess) {
+                drop_fresh();
+                return fail(CWSL_ERR_NOMEM, "phase table alloc: %s", cudaGetErrorString(err));
+            }
+            fresh[k] = tab;
+            new_inc.push_back(make_float2(g.ch[c].nco.phase_inc.real(), g.ch[c].nco.phase_inc.imag()));
+            new_tab.push_back(tab);
+        }
+        if (!new_tab.empty()) {
+            float2* d_inc = nullptr;
+            float2** d_tab = nullptr;
+            cudaError_t err = cudaMalloc(&d_inc, new_inc.size() * sizeof(float2));
+            if (err == cudaSuccess) err = cudaMalloc((void**)&d_tab, new_tab.size() * sizeof(float2*));
+            if (err == cudaSuccess) err = cudaMemcpy(d_inc, new_inc.data(), new_inc.size() * sizeof(float2), cudaMemcpyHostToDevice);
+            if (err == cudaSuccess) err = cudaMemcpy((void*)d_tab, new_tab.data(), new_tab.size() * sizeof(float2*), cudaMemcpyHostToDevice);
+            if (err == cudaSuccess) err = cwsl::launch_phase_tables(d_inc, d_tab, (uint32_t)new_tab.size(), length, rx->stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(rx->stream);
+            cudaFree(d_inc);
+            cudaFree((void*)d_tab);
+            if (err != cudaSuccess) {
+                drop_fresh();
+                return fail(err == cudaErrorMemoryAllocation ? CWSL_ERR_NOMEM : CWSL_ERR_CUDA, "phase table build: %s",
+                            cudaGetErrorString(err));
+            }
+        }
+        for (auto& kv : fresh) g_phase_cache[kv.first].table = kv.second;  // publish
+        for (uint32_t c = 0; c < C; ++c) {
+            const PhaseKey k{rx->device, rx->fs, g.ch[c].demod_freq, g.ch[c].usb, length};
+            PhaseEntry& e = g_phase_cache[k];
+            ++e.refs;
+            g.phase_keys.push_back(k);
+            ptrs[c] = e.table;
+        }
+    }
+    CK(cudaMemcpy((void*)g.d_phase, ptrs.data(), C * sizeof(float2*), cudaMemcpyHostToDevice));
+    g.committed = true;
+    return CWSL_OK;
+}
+
+// STFT-mode extras of a slot group, set up at its first STFT launch: the anchor table of the exact phase recurrence
+// (shared between groups with the same channel list) and the guard's scratch.
+int ensure_stft(cwsl_rx* rx, Group& g) {
+    const uint32_t C = (uint32_t)g.ch.size();
+    if (!g.d_anchors) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        AnchorEntry& e = g_anchor_cache[g.phase_keys];
+        if (!e.table) {
+            const uint32_t n_anchor = (uint32_t)(g.af_size / cwsl::kChanAnchorHops + 2);
+            float2* tab = nullptr;
+            cudaError_t err = commit_nosync() ? cudaSuccess : cudaDeviceSynchronize();
+            if (err == cudaSuccess) err = cudaMalloc(&tab, (size_t)n_anchor * C * sizeof(float2));
+            if (err == cudaSuccess) err = cwsl::launch_phase_anchors(g.d_phase, tab, C, n_anchor, cwsl::kChanAnchorHops, rx->stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(rx->stream);
+            if (err != cudaSuccess) {
+                cudaFree(tab);
+                g_anchor_cache.erase(g.phase_keys);
+                return fail(err == cudaErrorMemoryAllocation ? CWSL_ERR_NOMEM : CWSL_ERR_CUDA, "anchor table: %s",
+                            cudaGetErrorString(err));
+            }
+            e.table = tab;
+            e.n_anchor = n_anchor;
+        }
+        ++e.refs;
+        g.have_anchor_ref = true;
+        g.d_anchors = e.table;
+    }
+    if (!g.d_seg_scale) {
+        const uint32_t W = cwsl::fast_seg_blocks(g.tiles);
+        const uint32_t segs = (uint32_t)(g.af_size / W + 2);
+        if (!commit_nosync()) CK(cudaDeviceSynchronize());
+        CK(cudaMalloc(&g.d_seg_scale, segs * sizeof(float)));
+        CK(cudaMalloc(&g.d_seg_max, (size_t)segs * C * sizeof(unsigned)));
+        CK(cudaMalloc(&g.d_seg_energy, (size_t)segs * C * sizeof(unsigned)));
+        CK(cudaMalloc(&g.d_sel, (size_t)segs * C * sizeof(uint32_t)));
+        CK(cudaMalloc(&g.d_items, (size_t)segs * ((C + 31) / 32) * sizeof(cwsl::GuardItem)));
+        CK(cudaMalloc(&g.d_n_items, sizeof(unsigned)));
+        CK(cudaMemsetAsync(g.d_seg_max, 0, (size_t)segs * C * sizeof(unsigned), rx->stream));
+        CK(cudaMemsetAsync(g.d_seg_energy, 0, (size_t)segs * C * sizeof(unsigned), rx->stream));
+        CK(cudaMemsetAsync(g.d_n_items, 0, sizeof(unsigned), rx->stream));
+        g.max_segs = segs;
+    }
     return CWSL_OK;
 }
 
@@ -355,7 +493,12 @@ int ensure_ring(cwsl_rx* rx) {
         else
             blocks = rx->max_slot_blocks + 64;  // longest slot (+5 s) fits without intermediate demodulation
         const uint64_t quantum = std::max<uint64_t>(rx->sub, 4);
-        blocks = std::max<uint64_t>(blocks, 4 * (uint64_t)rx->sub + 64);
+        // The FAST / STFT modes demodulate whole segments only (fixed slot-relative positions, so that the result
+        // does not depend on the chunking); up to one segment (+31 blocks of history) of every open slot stays in
+        // the ring while the next push, at most half a ring long, arrives. ring_seconds is therefore a minimum.
+        uint64_t seg = 0;
+        for (const Group& g : rx->groups) seg = std::max<uint64_t>(seg, cwsl::fast_seg_blocks(g.tiles));
+        blocks = std::max<uint64_t>(blocks, 2 * seg + 4 * (uint64_t)rx->sub + 64);
         blocks = (blocks + quantum - 1) / quantum * quantum;
         rx->own_ring_blocks = (uint32_t)blocks;
         CK(cudaDeviceSynchronize());  // allocate on a quiet device, see commit()
@@ -392,9 +535,26 @@ uint32_t stft_min_channels() {
     return v;
 }
 
-int process_group(cwsl_rx* rx, Group& g) {
-    const uint64_t target = slot_target_blocks(rx, g);
+// Default threshold of the STFT dynamic-range guard, dB below the band's mean power (cwsl_guard.cu); the measured
+// float32-FFT floor is 1.7e-7 of the band's rms (-135 dB), 90 dB above it is -45 dB, 3 dB of margin.
+// CWSL_STFT_GUARD_DB overrides (0 = guard off).
+double default_guard_db() {
+    static const double v = [] {
+        const char* e = std::getenv("CWSL_STFT_GUARD_DB");
+        return e ? std::atof(e) : 42.0;
+    }();
+    return v;
+}
+
+// Demodulate what has been pushed for the group's open slot. EXACT: everything. FAST / STFT: whole segments only
+// unless `final` (the slot edge), so every launch starts on a segment boundary.
+int process_group(cwsl_rx* rx, Group& g, bool final) {
+    uint64_t target = slot_target_blocks(rx, g);
+    if (g.processed == 0) g.mode = rx->mode;  // the arithmetic mode is latched per slot
+    const uint32_t seg = g.mode == CWSL_MODE_EXACT ? 0u : cwsl::fast_seg_blocks(g.tiles);
+    if (seg && !final) target = target / seg * seg;
     if (target <= g.processed) return CWSL_OK;
+    if (seg && g.processed % seg != 0) return fail(CWSL_ERR_STATE, "internal: launch not on a segment boundary");
     // history still in the ring?
     const uint64_t first_needed = g.slot_start + (g.processed >= 31 ? g.processed - 31 : 0);
     if (rx->abs_written - first_needed > rx->ring_blocks)
@@ -414,15 +574,21 @@ int process_group(cwsl_rx* rx, Group& g) {
     p.audio = g.d_audio;
     p.af_stride = g.af_stride;
     p.maxbits = g.d_maxbits;
+    const bool stft = g.mode == CWSL_MODE_STFT && p.n_channels >= stft_min_channels() && p.ring_blocks >= 64;
+    // (IQ buffers shorter than two windows stay with the direct kernel)
+    if (stft) {
+        const int rc = ensure_stft(rx, g);
+        if (rc != CWSL_OK) return rc;
+    }
     // the post stream may still be normalising / copying the previous slot out of the buffers this launch rewrites
     if (rx->d2h_pending) CK(cudaStreamWaitEvent(rx->stream, rx->ev_d2h_done, 0));
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cwsl_rx::DemodEvents ev;
     if (rx->timing) {
-        e0 = get_event(rx);
-        e1 = get_event(rx);
-        CK(cudaEventRecord(e0, rx->stream));
+        ev.e0 = get_event(rx);
+        ev.e1 = get_event(rx);
+        CK(cudaEventRecord(ev.e0, rx->stream));
     }
-    if (rx->mode == CWSL_MODE_EXACT) {
+    if (g.mode == CWSL_MODE_EXACT) {
         // CWSL_EXACT_KERNEL=gather selects the independent one-thread-per-output implementation (cross-check)
         static const bool gather = [] {
             const char* e = std::getenv("CWSL_EXACT_KERNEL");
@@ -432,29 +598,65 @@ int process_group(cwsl_rx* rx, Group& g) {
             CK(cwsl::launch_demod_exact_gather(p, rx->stream));
         else
             CK(cwsl::launch_demod_exact(p, rx->stream));
-    }
-    else if (rx->mode == CWSL_MODE_STFT && p.n_channels >= stft_min_channels() && p.ring_blocks >= 64) {
-        // (IQ buffers shorter than two windows stay with the direct kernel)
-        // big channel groups: one FFT per hop shared by all channels, <= kChanMaxChannels channels per launch
+    } else if (stft) {
+        // big channel groups: one FFT per hop shared by all channels, <= kChanMaxChannels channels per launch;
+        // channel segments too close to the FFT's noise floor are redone by the direct-form kernel (cwsl_guard.cu)
+        const bool guard = rx->guard_db > 0;
+        cwsl::GuardLaunch gl;
+        gl.seg_blocks = seg;
+        gl.t2 = (float)std::pow(10.0, -rx->guard_db / 10.0);
+        gl.seg_scale = g.d_seg_scale;
+        gl.seg_max = g.d_seg_max;
+        gl.seg_energy = g.d_seg_energy;
+        gl.stat_stride = p.n_channels;
+        gl.sel = g.d_sel;
+        gl.sel_stride = p.n_channels;
+        gl.items = g.d_items;
+        gl.n_items = g.d_n_items;
+        gl.counters = g.d_counters;
+        if ((p.b1 - p.b0 + seg - 1) / seg > g.max_segs) return fail(CWSL_ERR_STATE, "internal: guard scratch too small");
+        if (guard) CK(cwsl::launch_guard_band_power(p, gl, rx->stream));
+        if (rx->timing) {
+            ev.e_pre = get_event(rx);
+            ev.e_main = get_event(rx);
+            CK(cudaEventRecord(ev.e_pre, rx->stream));
+        }
         for (uint32_t c0 = 0; c0 < p.n_channels; c0 += cwsl::kChanMaxChannels) {
             cwsl::DemodLaunch q = p;
             q.n_channels = std::min<uint32_t>(cwsl::kChanMaxChannels, p.n_channels - c0);
-            q.phase = p.phase + c0;
-            q.sign = p.sign + c0;
             q.audio = p.audio + (size_t)c0 * p.af_stride;
             q.maxbits = p.maxbits + c0;
             cwsl::ChanLaunch c;
             c.window = rx->chan_tables.window;
             c.twiddle = rx->chan_tables.twiddle;
             c.consts = g.d_chan + c0;
+            c.anchors = g.d_anchors + c0;
+            c.anchor_stride = p.n_channels;
+            if (guard) {
+                c.seg_blocks = seg;
+                c.seg_max = g.d_seg_max + c0;
+                c.seg_energy = g.d_seg_energy + c0;
+                c.seg_scale = g.d_seg_scale;
+                c.stat_stride = p.n_channels;
+            }
             CK(cwsl::launch_demod_chan(q, c, rx->stream));
         }
+        if (rx->timing) CK(cudaEventRecord(ev.e_main, rx->stream));
+        if (guard) {
+            CK(cwsl::launch_guard_select(p, gl, rx->stream));
+            cwsl::FastIndirect ind;
+            ind.items = g.d_items;
+            ind.n_items = g.d_n_items;
+            ind.sel = g.d_sel;
+            ind.sel_stride = p.n_channels;
+            CK(cwsl::launch_demod_fast(p, g.tiles, ind, rx->stream));
+        }
+    } else {
+        CK(cwsl::launch_demod_fast(p, g.tiles, cwsl::FastIndirect{}, rx->stream));
     }
-    else
-        CK(cwsl::launch_demod_fast(p, rx->stream));
     if (rx->timing) {
-        CK(cudaEventRecord(e1, rx->stream));
-        rx->ev_demod.emplace_back(e0, e1);
+        CK(cudaEventRecord(ev.e1, rx->stream));
+        rx->ev_demod.push_back(ev);
     }
     g.processed = target;
     return CWSL_OK;
@@ -480,7 +682,7 @@ int push_common(cwsl_rx* rx, const float* iq, size_t n_blocks, cudaMemcpyKind ki
         for (Group& g : rx->groups) {
             const uint64_t first_needed = g.slot_start + (g.processed >= 31 ? g.processed - 31 : 0);
             if (rx->abs_written + add - first_needed > rx->ring_blocks) {
-                rc = process_group(rx, g);
+                rc = process_group(rx, g, false);
                 if (rc != CWSL_OK) return rc;
             }
         }
@@ -640,6 +842,7 @@ cwsl_rx_t* cwsl_rx_create(int device, uint32_t sample_rate, uint32_t iq_len, dou
     rx->geo = geo;
     rx->sub = iq_len / geo.block_size;
     rx->ring_seconds = ring_seconds;
+    rx->guard_db = default_guard_db();
     // The post stream (normalise/quantise, max reset, D2H) gets the LOWEST priority: when its quantise kernel and the
     // next demodulation become runnable together, the block scheduler places the demodulator's CTAs first and the
     // HBM-bound quantise CTAs fill what is left of every SM, instead of the demodulator waiting for them to drain.
@@ -663,10 +866,9 @@ void cwsl_rx_destroy(cwsl_rx_t* rx) {
     if (rx->copy_stream) cudaStreamSynchronize(rx->copy_stream);
     for (Group& g : rx->groups) free_group_device(g);
     cudaFree(rx->d_ring);
-    for (auto& pr : rx->ev_demod) {
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
-    }
+    for (auto& ev : rx->ev_demod)
+        for (cudaEvent_t e : {ev.e0, ev.e_pre, ev.e_main, ev.e1})
+            if (e) cudaEventDestroy(e);
     for (auto& pr : rx->ev_quant) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -703,6 +905,12 @@ int cwsl_rx_enable_timing(cwsl_rx_t* rx, int on) {
     return CWSL_OK;
 }
 
+int cwsl_rx_set_stft_guard(cwsl_rx_t* rx, double db_below_band_power) {
+    if (!rx || !(db_below_band_power >= 0) || db_below_band_power > 200) return fail(CWSL_ERR_INVALID, "bad guard threshold");
+    rx->guard_db = db_below_band_power;
+    return CWSL_OK;
+}
+
 int cwsl_rx_add_group(cwsl_rx_t* rx, double period_s) {
     if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
     if (rx->committed) return fail(CWSL_ERR_STATE, "groups must be added before the first push");
@@ -716,10 +924,72 @@ int cwsl_rx_add_group(cwsl_rx_t* rx, double period_s) {
     return (int)rx->groups.size() - 1;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Replace a committed group's channel set between two slots: the new device state is built first (it takes its own
+// references on the shared phase tables), then the old one is released, so tables both sets use are never rebuilt.
+int rebuild_group(cwsl_rx* rx, Group& g, std::vector<ChannelHost> channels) {
+    if (channels.empty()) return fail(CWSL_ERR_STATE, "a slot group cannot lose its last channel");
+    CK(cudaStreamSynchronize(rx->stream));       // nothing may still read the old buffers
+    CK(cudaStreamSynchronize(rx->copy_stream));
+    rx->d2h_pending = false;
+    Group old = g;                               // (shallow: device pointers and cache references move to `old`)
+    g.ch = std::move(channels);
+    g.phase_keys.clear();
+    g.have_anchor_ref = false;
+    g.d_tone = nullptr;
+    g.d_phase = nullptr;
+    g.d_sign = g.d_scale = g.d_factor = g.d_maxval = g.d_audio = g.d_seg_scale = nullptr;
+    g.d_maxbits = g.d_seg_max = g.d_seg_energy = g.d_n_items = nullptr;
+    g.d_sel = nullptr;
+    g.d_items = nullptr;
+    g.d_counters = nullptr;
+    g.d_out = nullptr;
+    g.d_chan = nullptr;
+    g.d_anchors = nullptr;
+    g.max_segs = 0;
+    g.committed = false;
+    g.have_result = false;
+    const int rc = commit_group(rx, g);
+    if (rc != CWSL_OK) {                         // keep the old channel set alive
+        const std::string msg = g_last_error;
+        g = old;
+        g_last_error = msg;
+        return rc;
+    }
+    free_group_device(old);
+    // ring sizing depends on the group's segment length, which depends on its size: a grown group may need more
+    if (rx->d_ring && !rx->bound) {
+        uint64_t seg = 0;
+        for (const Group& h : rx->groups) seg = std::max<uint64_t>(seg, cwsl::fast_seg_blocks(h.tiles));
+        if (rx->own_ring_blocks < 2 * seg + 4 * (uint64_t)rx->sub + 64)
+            return fail(CWSL_ERR_STATE, "IQ ring too short for the grown slot group: create the receiver with ring_seconds >= %.2f",
+                        (double)(2 * seg + 4 * (uint64_t)rx->sub + 64) * rx->geo.block_size / rx->fs);
+    }
+    return CWSL_OK;
+}
+
+int apply_pending(cwsl_rx* rx, Group& g) {
+    if (g.pending_add.empty() && g.pending_remove.empty()) return CWSL_OK;
+    std::vector<ChannelHost> next;
+    std::set<int> gone(g.pending_remove.begin(), g.pending_remove.end());
+    for (size_t c = 0; c < g.ch.size(); ++c)
+        if (!gone.count((int)c)) next.push_back(g.ch[c]);
+    for (ChannelHost& c : g.pending_add) next.push_back(std::move(c));
+    g.pending_add.clear();
+    g.pending_remove.clear();
+    return rebuild_group(rx, g, std::move(next));
+}
+
+}  // namespace
+
+extern "C" {
+
 int cwsl_rx_add_channel(cwsl_rx_t* rx, int group, int32_t demod_freq_hz, int is_usb, float scale) {
     Group* g = get_group(rx, group);
     if (!g) return CWSL_ERR_INVALID;
-    if (rx->committed) return fail(CWSL_ERR_STATE, "channels must be added before the first push");
     if (!(scale > 0.0f) || scale > 1.0f)  // source/CWSL_DIGI.cpp:952-978
         return fail(CWSL_ERR_INVALID, "audio scale factor %g outside (0, 1]", (double)scale);
     ChannelHost ch;
@@ -728,10 +998,43 @@ int cwsl_rx_add_channel(cwsl_rx_t* rx, int group, int32_t demod_freq_hz, int is_
     ch.scale = scale;
     if (!cwsl::nco_tables(rx->geo, demod_freq_hz, is_usb != 0, &ch.nco))
         return fail(CWSL_ERR_INVALID, "Signal outside of band (demod %d Hz at Fs %u)", demod_freq_hz, rx->fs);
-    if (g->ch.size() >= 65535)  // channels are a grid dimension of the normalise/quantise launch
+    const size_t after = g->ch.size() - g->pending_remove.size() + g->pending_add.size();
+    if (after >= 65535)  // channels are a grid dimension of the normalise/quantise launch
         return fail(CWSL_ERR_INVALID, "at most 65535 channels per slot group");
-    g->ch.push_back(std::move(ch));
-    return (int)g->ch.size() - 1;
+    if (!rx->committed) {
+        g->ch.push_back(std::move(ch));
+        return (int)g->ch.size() - 1;
+    }
+    // Running receiver (a decoder instance restarted on this band, source/CWSL_DIGI.cpp:1217-1226): the channel joins
+    // at the group's next slot edge; between slots that is now.
+    DeviceGuard dg(rx->device);
+    if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
+    g->pending_add.push_back(std::move(ch));
+    const int index = (int)after;
+    if (g->iq_blocks == 0 && g->processed == 0) {
+        const int rc = apply_pending(rx, *g);
+        if (rc != CWSL_OK) return rc;
+    }
+    return index;
+}
+
+int cwsl_rx_remove_channel(cwsl_rx_t* rx, int group, int channel) {
+    Group* g = get_group(rx, group);
+    if (!g) return CWSL_ERR_INVALID;
+    if (channel < 0 || channel >= (int)g->ch.size()) return fail(CWSL_ERR_INVALID, "bad channel %d", channel);
+    if (std::count(g->pending_remove.begin(), g->pending_remove.end(), channel))
+        return fail(CWSL_ERR_STATE, "channel %d is already being removed", channel);
+    if (g->ch.size() - g->pending_remove.size() + g->pending_add.size() <= 1)
+        return fail(CWSL_ERR_STATE, "a slot group cannot lose its last channel");
+    if (!rx->committed) {
+        g->ch.erase(g->ch.begin() + channel);
+        return CWSL_OK;
+    }
+    DeviceGuard dg(rx->device);
+    if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
+    g->pending_remove.push_back(channel);
+    if (g->iq_blocks == 0 && g->processed == 0) return apply_pending(rx, *g);
+    return CWSL_OK;
 }
 
 int cwsl_rx_num_groups(const cwsl_rx_t* rx) { return rx ? (int)rx->groups.size() : CWSL_ERR_INVALID; }
@@ -783,21 +1086,23 @@ int cwsl_rx_process(cwsl_rx_t* rx, int group) {
     if (rc != CWSL_OK) return rc;
     if (group >= 0) {
         Group* g = get_group(rx, group);
-        return g ? process_group(rx, *g) : CWSL_ERR_INVALID;
+        return g ? process_group(rx, *g, false) : CWSL_ERR_INVALID;
     }
     for (Group& g : rx->groups)
-        if ((rc = process_group(rx, g)) != CWSL_OK) return rc;
+        if ((rc = process_group(rx, g, false)) != CWSL_OK) return rc;
     return CWSL_OK;
 }
 
-int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_index) {
-    Group* g = get_group(rx, group);
-    if (!g) return CWSL_ERR_INVALID;
-    DeviceGuard dg(rx->device);
-    if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
-    int rc = commit(rx);
+}  // extern "C"
+
+namespace {
+
+// Kernels and copies of a slot edge; the caller resets the slot whatever this returns.
+int end_slot_work(cwsl_rx* rx, Group* g, int16_t* out_i16) {
+    if (const char* e = std::getenv("CWSL_TEST_FAIL_END_SLOT"); e && e[0] == '1')  // fault injection for the tests
+        return fail(CWSL_ERR_CUDA, "injected failure (CWSL_TEST_FAIL_END_SLOT)");
+    int rc = process_group(rx, *g, true);
     if (rc != CWSL_OK) return rc;
-    if ((rc = process_group(rx, *g)) != CWSL_OK) return rc;
     const uint32_t C = (uint32_t)g->ch.size();
     cwsl::QuantLaunch q;
     q.audio = g->d_audio;
@@ -824,7 +1129,8 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
         CK(cudaEventRecord(e0, rx->copy_stream));
     }
     CK(cwsl::launch_quantise(q, rx->copy_stream));
-    CK(cwsl::launch_clear_u32(g->d_maxbits, C, rx->copy_stream));  // next slot starts from max|x| = 0
+    // next slot starts from max|x| = 0; the guard's counters roll over to "last finished slot"
+    CK(cwsl::launch_clear_u32(g->d_maxbits, C, g->d_counters, rx->copy_stream));
     if (rx->timing) {
         CK(cudaEventRecord(e1, rx->copy_stream));
         rx->ev_quant.emplace_back(e0, e1);
@@ -832,7 +1138,7 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
     if (out_i16) {
         size_t cols = g->af_size;  // default: the whole buffer, zero tail included
         {
-            std::lock_guard<std::mutex> lk(g_mu);
+            std::lock_guard<std::mutex> lk(g_host_mu);
             const uintptr_t a = reinterpret_cast<uintptr_t>(out_i16);
             auto it = g_host_regions.upper_bound(a);
             if (it != g_host_regions.begin()) {
@@ -865,14 +1171,45 @@ int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_i
     }
     CK(cudaEventRecord(rx->ev_d2h_done, rx->copy_stream));
     rx->d2h_pending = true;
-    if (write_index) *write_index = (size_t)g->processed;
-    g->last_write_index = (size_t)g->processed;
-    g->have_result = true;
-    // slot reset: fresh SSBD per slot (source/Instance.cpp:251)
+    return CWSL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_index) {
+    Group* g = get_group(rx, group);
+    if (!g) return CWSL_ERR_INVALID;
+    DeviceGuard dg(rx->device);
+    if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
+    int rc = commit(rx);
+    if (rc != CWSL_OK) return rc;
+    rc = end_slot_work(rx, g, out_i16);
+    if (rc == CWSL_OK) {
+        if (write_index) *write_index = (size_t)g->processed;
+        g->last_write_index = (size_t)g->processed;
+        g->have_result = true;
+    } else {
+        // A failed slot is LOST, not stuck: the reference logs the error and carries on with the next slot
+        // (source/Receiver.hpp:222-229, source/Instance.cpp:268-271). Whatever part of it reached the max is dropped.
+        const std::string msg = g_last_error;
+        if (write_index) *write_index = 0;
+        g->have_result = false;
+        if (g->d_maxbits) cudaMemsetAsync(g->d_maxbits, 0, g->ch.size() * sizeof(unsigned), rx->stream);
+        cudaGetLastError();
+        g_last_error = msg;
+    }
+    // slot reset: fresh SSBD per slot (source/Instance.cpp:251) -- on the error path as well
     g->slot_start = rx->abs_written;
     g->processed = 0;
     g->iq_blocks = 0;
-    return CWSL_OK;
+    if (rc == CWSL_OK && (!g->pending_add.empty() || !g->pending_remove.empty())) {
+        // the finished slot's int16 result must stay readable: it is copied out before the buffers are replaced
+        if (!out_i16) return fail(CWSL_ERR_STATE, "channel-set change pending: this slot's result must be taken to the host");
+        rc = apply_pending(rx, *g);
+    }
+    return rc;
 }
 
 const int16_t* cwsl_rx_device_audio(const cwsl_rx_t* rx, int group) {
@@ -939,32 +1276,76 @@ int cwsl_rx_wait_output(cwsl_rx_t* rx) {
 
 void* cwsl_rx_stream(cwsl_rx_t* rx) { return rx ? (void*)rx->stream : nullptr; }
 
-int cwsl_rx_kernel_times(cwsl_rx_t* rx, float* demod_ms, float* quant_ms, int* demod_launches, int* quant_launches) {
+int cwsl_rx_kernel_times_ex(cwsl_rx_t* rx, float ms[5], int launches[2]) {
     if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
     DeviceGuard dg(rx->device);
     CK(cudaStreamSynchronize(rx->stream));
     CK(cudaStreamSynchronize(rx->copy_stream));
-    float dsum = 0, qsum = 0;
-    for (auto& pr : rx->ev_demod) {
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
-        dsum += ms;
-        rx->ev_pool.push_back(pr.first);
-        rx->ev_pool.push_back(pr.second);
+    float dsum = 0, qsum = 0, pre = 0, main_ms = 0, post = 0;
+    for (auto& ev : rx->ev_demod) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, ev.e0, ev.e1));
+        dsum += t;
+        if (ev.e_pre && ev.e_main) {  // STFT launch: guard prologue | channelizer | guard selection + direct-form redo
+            CK(cudaEventElapsedTime(&t, ev.e0, ev.e_pre));
+            pre += t;
+            CK(cudaEventElapsedTime(&t, ev.e_pre, ev.e_main));
+            main_ms += t;
+            CK(cudaEventElapsedTime(&t, ev.e_main, ev.e1));
+            post += t;
+        } else {
+            CK(cudaEventElapsedTime(&t, ev.e0, ev.e1));
+            main_ms += t;
+        }
+        for (cudaEvent_t e : {ev.e0, ev.e_pre, ev.e_main, ev.e1})
+            if (e) rx->ev_pool.push_back(e);
     }
     for (auto& pr : rx->ev_quant) {
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
-        qsum += ms;
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, pr.first, pr.second));
+        qsum += t;
         rx->ev_pool.push_back(pr.first);
         rx->ev_pool.push_back(pr.second);
     }
-    if (demod_ms) *demod_ms = dsum;
-    if (quant_ms) *quant_ms = qsum;
-    if (demod_launches) *demod_launches = (int)rx->ev_demod.size();
-    if (quant_launches) *quant_launches = (int)rx->ev_quant.size();
+    if (ms) {
+        ms[0] = dsum;
+        ms[1] = qsum;
+        ms[2] = main_ms;
+        ms[3] = pre;
+        ms[4] = post;
+    }
+    if (launches) {
+        launches[0] = (int)rx->ev_demod.size();
+        launches[1] = (int)rx->ev_quant.size();
+    }
     rx->ev_demod.clear();
     rx->ev_quant.clear();
+    return CWSL_OK;
+}
+
+int cwsl_rx_kernel_times(cwsl_rx_t* rx, float* demod_ms, float* quant_ms, int* demod_launches, int* quant_launches) {
+    float ms[5] = {0, 0, 0, 0, 0};
+    int n[2] = {0, 0};
+    const int rc = cwsl_rx_kernel_times_ex(rx, ms, n);
+    if (rc != CWSL_OK) return rc;
+    if (demod_ms) *demod_ms = ms[0];
+    if (quant_ms) *quant_ms = ms[1];
+    if (demod_launches) *demod_launches = n[0];
+    if (quant_launches) *quant_launches = n[1];
+    return CWSL_OK;
+}
+
+int cwsl_rx_guard_stats(cwsl_rx_t* rx, int group, uint64_t* decided, uint64_t* redone) {
+    Group* g = get_group(rx, group);
+    if (!g) return CWSL_ERR_INVALID;
+    if (!g->have_result) return fail(CWSL_ERR_STATE, "no finished slot available");
+    DeviceGuard dg(rx->device);
+    CK(cudaStreamSynchronize(rx->stream));
+    CK(cudaStreamSynchronize(rx->copy_stream));
+    unsigned long long v[4] = {0, 0, 0, 0};
+    if (g->d_counters) CK(cudaMemcpy(v, g->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
+    if (decided) *decided = v[2];
+    if (redone) *redone = v[3];
     return CWSL_OK;
 }
 
@@ -980,7 +1361,7 @@ void* cwsl_host_alloc(size_t bytes) {
         return nullptr;
     }
     std::memset(p, 0, bytes);
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(g_host_mu);
     g_host_regions[reinterpret_cast<uintptr_t>(p)].bytes = bytes;
     return p;
 }
@@ -988,7 +1369,7 @@ void* cwsl_host_alloc(size_t bytes) {
 void cwsl_host_free(void* p) {
     if (!p) return;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
+        std::lock_guard<std::mutex> lk(g_host_mu);
         g_host_regions.erase(reinterpret_cast<uintptr_t>(p));
     }
     cudaFreeHost(p);

@@ -58,7 +58,6 @@ struct ChanGeo {
     // float2 per hop buffer: A rows of 34 during the transpose, N (+8 wrapped) bins after; the 8-row geometry gets 8
     // more so that the two hops of a half-warp sit 16 banks apart
     static constexpr int kHop = kA * kRow + (kA == 8 ? 8 : 0);
-    static constexpr int kAnchorEvery = 16 / kHW;  // batches between phase-table anchors (128 hops)
     static_assert(kN + 8 <= kHop, "wrapped stencil bins must fit");
 };
 
@@ -156,15 +155,35 @@ constexpr int kFftWarps = 8;
 constexpr int kFftThreads = 32 * kFftWarps;
 constexpr int kIntThreads = 256;  // interpolation threads per CTA, each owns up to KC channels for the whole launch
 constexpr int kThreads = kFftThreads + kIntThreads;
+// IQ staging ring in shared memory: stages of one batch worth of new samples (HB blocks = 1 KB at every rate),
+// brought in by the TMA bulk-copy engine kIqPrefetch batches ahead of the FFT warps. 16 stages: a batch reads the
+// newest stage and the <= 4 before it (the 31 blocks of filter history), 3 are in flight, and the FFT warps are never
+// more than kBufs batches apart (they meet the interpolation warps at the spectrum ring), so a stage is overwritten
+// long after its last reader -- no "empty" barrier is needed.
+constexpr int kIqStages = 16;
+constexpr int kIqPrefetch = 3;
 template <int BS>
-constexpr size_t spec_bytes() {  // 3 buffers x (8 FFT warps x HW hops) x hop buffer: 204 KB at every rate
+__host__ __device__ constexpr size_t spec_bytes() {  // 3 buffers x (8 FFT warps x HW hops) x hop buffer: 204 KB at every rate
     return (size_t)kBufs * ChanGeo<BS>::kHB * ChanGeo<BS>::kHop * 8;
+}
+template <int BS>
+__host__ __device__ constexpr size_t iq_stage_bytes() { return (size_t)ChanGeo<BS>::kHB * BS * 8; }  // 1 KB
+template <int BS>
+__host__ __device__ constexpr size_t chan_smem_bytes() { return spec_bytes<BS>() + kIqStages * iq_stage_bytes<BS>() + kIqStages * 8; }
+
+// Complex multiply with a FIXED contraction pattern: the per-hop NCO step R <- R * phase_inc between anchors must
+// give the same bits wherever it is evaluated (in the hop loop, or replayed from the anchor at the start of a CTA's
+// run), or the output would depend on how a slot is cut into launches.
+__device__ __forceinline__ float2 cmul_fix(float2 a, float2 b) {
+    return make_float2(__fmaf_rn(a.x, b.x, -__fmul_rn(a.y, b.y)), __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x)));
 }
 
 // Persistent, warp-specialised: CTA j owns a contiguous run of batches (kHB hops each). Warps 0..7 (producers)
 // compute the spectra of the batch's hops into spectrum buffer s; warps 8..15 (consumers) read every channel's
 // frequency off those spectra while the producers are already transforming the next batches. Hand-over by named
-// barriers (bar.arrive / bar.sync), no __syncthreads in the loop.
+// barriers (bar.arrive / bar.sync), no __syncthreads in the loop. The IQ samples reach the FFT warps through a
+// shared-memory ring filled by cp.async.bulk (TMA) with mbarrier completion: each sample crosses L2 -> SM once per
+// CTA run instead of once per hop that covers it (32x).
 // 104 registers x 512 threads leave room on every SM for CTAs of the (HBM-bound) quantise kernel of the previous
 // receiver, which then runs underneath this (shared-memory-bound) kernel instead of after it.
 template <int BS, int KC>
@@ -172,30 +191,57 @@ __global__ void __maxnreg__(104)
     demod_chan_kernel(DemodLaunch p, ChanLaunch c, uint32_t n_batches, uint32_t batches_per_cta) {
     using G = ChanGeo<BS>;
     constexpr int A = G::kA, HW = G::kHW, HB = G::kHB, HOP = G::kHop, N = G::kN;
-    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int P0 = (31 + HB - 1) / HB;   // stages of filter history in front of a batch's own stage: 4 / 2 / 1
+    constexpr uint32_t RB = kIqStages * HB;  // SSBD blocks in the shared-memory IQ ring (a power of two)
+    constexpr uint32_t kStageBytes = (uint32_t)iq_stage_bytes<BS>();
+    static_assert((RB & (RB - 1)) == 0 && P0 * HB >= 31 && P0 + 1 + kIqPrefetch + kBufs + 2 <= kIqStages, "IQ ring geometry");
+    extern __shared__ __align__(128) unsigned char smem[];
     float2* spec = reinterpret_cast<float2*>(smem);
+    float2* iq_s = reinterpret_cast<float2*>(smem + spec_bytes<BS>());
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + spec_bytes<BS>() + kIqStages * iq_stage_bytes<BS>());
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint32_t s0 = blockIdx.x * batches_per_cta;
     const uint32_t s1 = min(n_batches, s0 + batches_per_cta);
     if (s0 >= s1) return;
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < kIqStages; ++i) mbar_init(smem_u32(bars + i), 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
 
     if (warp < (uint32_t)kFftWarps) {
         // ================= producers: warp w transforms hops w*HW .. w*HW+HW-1 of every batch =================
+        const uint32_t nb = s1 - s0;
+        // local stage l of this CTA holds the slot-relative blocks kbase0 + HB*l .. +HB-1; batch `it` (its own new
+        // samples are stage P0 + it) reads stages it .. it + P0
+        const long long kbase0 = (long long)p.b0 + ((long long)s0 - P0) * HB;
+        auto issue_stage = [&](uint32_t l) {
+            long long m = ((long long)p.ring_off + kbase0 + (long long)l * HB) % (long long)p.ring_blocks;
+            if (m < 0) m += p.ring_blocks;  // (blocks before the slot: whatever the ring holds, masked below)
+            const uint32_t row = (uint32_t)m, slot = l % kIqStages;
+            const uint32_t dst = smem_u32(iq_s + (size_t)slot * HB * BS), bar_a = smem_u32(bars + slot);
+            mbar_arrive_expect_tx(bar_a, kStageBytes);
+            const uint32_t first = min((uint32_t)HB, p.ring_blocks - row);  // the IQ ring may wrap inside the stage
+            tma_bulk_g2s(dst, p.iq_ring + (size_t)row * BS, first * BS * 8u, bar_a);
+            if (first < (uint32_t)HB) tma_bulk_g2s(dst + first * BS * 8u, p.iq_ring, (HB - first) * BS * 8u, bar_a);
+        };
+        if (t == 0)
+            for (uint32_t l = 0; l <= (uint32_t)P0 + min((uint32_t)kIqPrefetch, nb - 1); ++l) issue_stage(l);
         // window of hop b = IQ blocks b-31 .. b (BS samples each); element j = 32 j1 + lane of the window sits in
         // block b-31 + j1*(32/BS) + lane/BS, sample lane % BS
         long long blk = (long long)p.b0 + (long long)s0 * HB + (long long)warp * HW - 31 + (long long)(lane / BS);
-        uint32_t row;
-        {
-            long long m = ((long long)p.ring_off + blk) % (long long)p.ring_blocks;
-            if (m < 0) m += p.ring_blocks;
-            row = (uint32_t)m;
-        }
+        uint32_t lb = (uint32_t)P0 * HB + warp * HW - 31 + lane / BS;  // the same block, counted from kbase0
         float wv[A / 2];  // this lane's window taps (constant over the launch)
 #pragma unroll
         for (int j1 = 0; j1 < A / 2; ++j1) wv[j1] = __ldg(c.window + 32 * j1 + lane);
-        uint32_t s = 0;
-        for (uint32_t i = s0; i < s1; ++i, s = (s + 1 == (uint32_t)kBufs) ? 0u : s + 1) {
-            if (i - s0 >= (uint32_t)kBufs) bar_sync(kBarEmpty + s, kThreads);  // consumers are done with this buffer
+        uint32_t s = 0, waited = 0;
+        for (uint32_t it = 0; it < nb; ++it, s = (s + 1 == (uint32_t)kBufs) ? 0u : s + 1) {
+            if (t == 0 && it > 0 && it + kIqPrefetch < nb) issue_stage((uint32_t)P0 + it + kIqPrefetch);
+            while (waited <= (uint32_t)P0 + it) {  // stages arrive in order; each is waited for once
+                mbar_wait(smem_u32(bars + (waited % kIqStages)), (waited / kIqStages) & 1u);
+                ++waited;
+            }
             float2* wbuf = spec + ((size_t)s * HB + (size_t)warp * HW) * HOP;  // this warp's HW hop buffers
             float2 v[32];
             // pass 1: lane = j2; per hop an A-point DFT over j1 of u[32 j1 + j2], u = x * window (j1 >= A/2: zero padding)
@@ -204,14 +250,13 @@ __global__ void __maxnreg__(104)
 #pragma unroll
                 for (int j1 = 0; j1 < A / 2; ++j1) {
                     const int boff = sub + j1 * (32 / BS);     // block offset of this element from the lane's base block
-                    uint32_t r = row + boff;                   // < 2 * ring_blocks
-                    if (r >= p.ring_blocks) r -= p.ring_blocks;
-                    float2 x = make_float2(0.0f, 0.0f);
-                    if (blk + boff >= 0) x = __ldg(p.iq_ring + (size_t)r * BS + (lane % BS));  // zero history before the slot
+                    float2 x = iq_s[(size_t)((lb + boff) & (RB - 1u)) * BS + (lane % BS)];
+                    if (blk + boff < 0) x = make_float2(0.0f, 0.0f);  // zero history before the slot (fresh SSBD)
                     v[sub * A + j1] = fmul2(x, bc(wv[j1]));
                 }
             }
             fft_dif_all<A, true>(v);
+            if (it >= (uint32_t)kBufs) bar_sync(kBarEmpty + s, kThreads);  // consumers are done with this buffer
             // twiddle W_N^(j2 q1) * i^q1 and transpose through the hop buffer (rows of 34: conflict-free both ways)
 #pragma unroll
             for (int sub = 0; sub < HW; ++sub) {
@@ -241,48 +286,89 @@ __global__ void __maxnreg__(104)
             if (q1 < 8) buf[N + q1] = v[0];
             bar_arrive(kBarFull + s, kThreads);
             blk += HB;
-            row += HB;
-            if (row >= p.ring_blocks) row -= p.ring_blocks;
+            lb += HB;
         }
     } else {
         // ================= consumers: thread owns channels tid, tid+256, ... =================
         const uint32_t tid = t - kFftThreads;
         uint32_t off[KC];      // byte offset of the channel's first stencil bin inside a hop buffer
         float wg[KC][8];       // interpolation weights
-        float2 rot[KC], pinc[KC], R[KC];
+        float2 pinc[KC], R[KC];
         float sgn[KC], mx[KC];
-        bool have[KC];
+        uint32_t ea[KC];       // guard: integer sum of the scaled octet energies of the current segment
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             const uint32_t ch = tid + k * kIntThreads;
-            have[k] = ch < p.n_channels;
-            const float4* kc = reinterpret_cast<const float4*>(c.consts + (have[k] ? ch : 0));
+            const float4* kc = reinterpret_cast<const float4*>(c.consts + (ch < p.n_channels ? ch : 0));
             const float4 k0 = __ldg(kc), k1 = __ldg(kc + 1), k2 = __ldg(kc + 2), k3 = __ldg(kc + 3);
             off[k] = ((uint32_t)__float_as_int(k0.x) & (uint32_t)(N - 1)) * 8u;
             sgn[k] = k0.y;
-            rot[k] = make_float2(k0.z, k0.w);
             wg[k][0] = k1.x, wg[k][1] = k1.y, wg[k][2] = k1.z, wg[k][3] = k1.w;
             wg[k][4] = k2.x, wg[k][5] = k2.y, wg[k][6] = k2.z, wg[k][7] = k2.w;
             pinc[k] = make_float2(k3.x, k3.y);
             R[k] = make_float2(0.0f, 0.0f);
             mx[k] = 0.0f;
+            ea[k] = 0u;
         }
+        // R = P_c[128 a] * rot_c from the exact recurrence (anchor table), then R <- R * phase_inc per hop
+        auto anchor = [&](int k, uint32_t a) {
+            const uint32_t ch = tid + k * kIntThreads;
+            const float2 P = __ldg(c.anchors + (size_t)a * c.anchor_stride + ch);
+            const float4 k0 = __ldg(reinterpret_cast<const float4*>(c.consts + ch));  // rot = (z, w); needed here only
+            return cmul_fix(P, make_float2(k0.z, k0.w));
+        };
+        const uint32_t bb0 = p.b0 + s0 * HB;
+        {   // a run that starts between two anchors replays the steps from the anchor before it: same bits as a run
+            // that came through them
+            const uint32_t a0 = bb0 / kChanAnchorHops, n_replay = bb0 % kChanAnchorHops;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (tid + k * kIntThreads >= p.n_channels) continue;
+                float2 r = anchor(k, a0);
+                for (uint32_t j = 0; j < n_replay; ++j) r = cmul_fix(r, pinc[k]);
+                R[k] = r;
+            }
+        }
+        // dynamic-range guard statistics (cwsl_guard.cu): per segment max|y| and an integer energy sum
+        const bool guard = c.seg_blocks != 0u;
+        uint32_t cur_seg = guard ? (bb0 - p.b0) / c.seg_blocks : 0u;
+        uint32_t next_seg_b = guard ? p.b0 + (cur_seg + 1u) * c.seg_blocks : 0xffffffffu;
+        float s2 = guard ? __ldg(c.seg_scale + cur_seg) : 0.0f;
+        auto flush = [&]() {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const uint32_t ch = tid + k * kIntThreads;
+                if (ch >= p.n_channels) continue;
+                const unsigned bits = __float_as_uint(mx[k]);
+                if (guard) {
+                    const size_t i = (size_t)cur_seg * c.stat_stride + ch;
+                    if (bits != 0u) atomicMax(c.seg_max + i, bits);
+                    if (ea[k] != 0u) atomicAdd(c.seg_energy + i, ea[k]);
+                } else if (bits != 0u && bits > __ldcg(p.maxbits + ch)) {
+                    atomicMax(p.maxbits + ch, bits);
+                }
+                mx[k] = 0.0f;
+                ea[k] = 0u;
+            }
+        };
         uint32_t s = 0;
         for (uint32_t i = s0; i < s1; ++i, s = (s + 1 == (uint32_t)kBufs) ? 0u : s + 1) {
             const uint32_t bb = p.b0 + i * HB;
-            if (((i - s0) % G::kAnchorEvery) == 0) {
-                // R = P_c[bb] * rot_c from the exact table; between anchors R *= phase_inc per hop
+            if (i != s0 && (bb % kChanAnchorHops) == 0u) {
 #pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    if (!have[k]) continue;
-                    const float2 P = __ldg(p.phase[tid + k * kIntThreads] + bb);
-                    R[k] = make_float2(P.x * rot[k].x - P.y * rot[k].y, P.x * rot[k].y + P.y * rot[k].x);
-                }
+                for (int k = 0; k < KC; ++k)
+                    if (tid + k * kIntThreads < p.n_channels) R[k] = anchor(k, bb / kChanAnchorHops);
+            }
+            if (bb >= next_seg_b) {  // (segments are multiples of 32 hops: a batch never straddles two)
+                flush();
+                ++cur_seg;
+                next_seg_b += c.seg_blocks;
+                s2 = __ldg(c.seg_scale + cur_seg);
             }
             bar_sync(kBarFull + s, kThreads);
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-                if (!have[k]) continue;
+                if (tid + k * kIntThreads >= p.n_channels) continue;
 #pragma unroll 1
                 for (int oct = 0; oct < HB / 8; ++oct) {  // eight hops at a time: one 32-byte store per channel
                     const uint32_t b8 = bb + 8 * oct;
@@ -301,40 +387,45 @@ __global__ void __maxnreg__(104)
                         const float2 r = R[k];
                         // audio[b] = {+Re, -Im*sign, -Re, +Im*sign}[b & 3] of acc*R; b8 is a multiple of 4
                         float o;
-                        if ((h & 3) == 0) o = acc.x * r.x - acc.y * r.y;
-                        else if ((h & 3) == 1) o = -(acc.x * r.y + acc.y * r.x) * sgn[k];
-                        else if ((h & 3) == 2) o = -(acc.x * r.x - acc.y * r.y);
-                        else o = (acc.x * r.y + acc.y * r.x) * sgn[k];
+                        if ((h & 3) == 0) o = __fmaf_rn(acc.x, r.x, -__fmul_rn(acc.y, r.y));
+                        else if ((h & 3) == 1) o = -__fmaf_rn(acc.x, r.y, __fmul_rn(acc.y, r.x)) * sgn[k];
+                        else if ((h & 3) == 2) o = -__fmaf_rn(acc.x, r.x, -__fmul_rn(acc.y, r.y));
+                        else o = __fmaf_rn(acc.x, r.y, __fmul_rn(acc.y, r.x)) * sgn[k];
                         out[h] = o;
-                        R[k] = make_float2(r.x * pinc[k].x - r.y * pinc[k].y, r.x * pinc[k].y + r.y * pinc[k].x);
+                        R[k] = cmul_fix(r, pinc[k]);
                     }
                     float* dst = p.audio + (size_t)(tid + k * kIntThreads) * p.af_stride + b8;
+                    float e8 = 0.0f;
                     if (b8 + 8 <= p.b1 && (b8 & 7u) == 0) {  // whole octet, 32-byte aligned row segment
                         stg256(dst, out);
                         float m = mx[k];
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) m = fmaxf(m, fabsf(out[h]));
+                        for (int h = 0; h < 8; ++h) {
+                            m = fmaxf(m, fabsf(out[h]));
+                            e8 = __fmaf_rn(out[h], out[h], e8);
+                        }
                         mx[k] = m;
                     } else {
 #pragma unroll
                         for (int h4 = 0; h4 < 8; h4 += 4) {
                             if (b8 + h4 < p.b1) {  // b1 is a multiple of 4
                                 *reinterpret_cast<float4*>(dst + h4) = make_float4(out[h4], out[h4 + 1], out[h4 + 2], out[h4 + 3]);
-                                mx[k] = fmaxf(mx[k], fmaxf(fmaxf(fabsf(out[h4]), fabsf(out[h4 + 1])), fmaxf(fabsf(out[h4 + 2]), fabsf(out[h4 + 3]))));
+#pragma unroll
+                                for (int h = h4; h < h4 + 4; ++h) {
+                                    mx[k] = fmaxf(mx[k], fabsf(out[h]));
+                                    e8 = __fmaf_rn(out[h], out[h], e8);
+                                }
                             }
                         }
                     }
+                    // scaled so that the guard's keep-threshold is 128 per hop on average; the integer sum is exact,
+                    // hence independent of how the segment is spread over CTAs and launches
+                    if (guard) ea[k] += __float2uint_rz(fminf(__fmul_rn(e8, s2), 1048576.0f));
                 }
             }
             if (i + kBufs < s1) bar_arrive(kBarEmpty + s, kThreads);  // (nobody waits for the last ones)
         }
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            if (!have[k]) continue;
-            const unsigned bits = __float_as_uint(mx[k]);
-            unsigned* dst = p.maxbits + tid + k * kIntThreads;
-            if (bits != 0 && bits > __ldcg(dst)) atomicMax(dst, bits);
-        }
+        flush();
     }
 }
 
@@ -359,13 +450,13 @@ cudaError_t launch_t(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) 
     constexpr int HB = ChanGeo<BS>::kHB;
     auto kern = demod_chan_kernel<BS, KC>;
     int sms = 0;
-    cudaError_t e = prepare(reinterpret_cast<const void*>(kern), spec_bytes<BS>(), &sms);
+    cudaError_t e = prepare(reinterpret_cast<const void*>(kern), chan_smem_bytes<BS>(), &sms);
     if (e != cudaSuccess) return e;
     const uint32_t n_batches = (p.b1 - p.b0 + HB - 1) / HB;
     // one CTA per SM, contiguous runs of batches (anchored phase recurrence, sequential IQ reads)
     const uint32_t per_cta = (n_batches + (uint32_t)sms - 1) / (uint32_t)sms;
     const uint32_t grid = (n_batches + per_cta - 1) / per_cta;
-    kern<<<grid, kThreads, spec_bytes<BS>(), s>>>(p, c, n_batches, per_cta);
+    kern<<<grid, kThreads, chan_smem_bytes<BS>(), s>>>(p, c, n_batches, per_cta);
     return cudaGetLastError();
 }
 
@@ -385,7 +476,8 @@ uint32_t chan_max_channels() { return kChanMaxChannels; }
 
 cudaError_t launch_demod_chan(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
     if (c.taps != kChanTaps || p.n_channels == 0 || p.n_channels > kChanMaxChannels || p.ring_blocks < 64 ||
-        (p.b0 & 3u) || (p.b1 & 3u) || (p.af_stride & 7u))
+        (p.b0 & 31u) || (p.b1 & 3u) || (p.af_stride & 7u) || !c.anchors ||
+        (c.seg_blocks != 0u && (p.b0 % c.seg_blocks != 0u || (c.seg_blocks & 31u) || !c.seg_max || !c.seg_energy || !c.seg_scale)))
         return cudaErrorInvalidValue;
     if (p.b1 <= p.b0) return cudaSuccess;
     switch (p.block_size) {

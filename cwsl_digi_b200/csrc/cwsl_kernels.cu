@@ -199,15 +199,20 @@ struct FastCfg {
     static constexpr size_t kCarryBytes = (size_t)G * 31 * 8;
     // 2 CTAs/SM need 2*(kSmem + 1 KB reserved) <= 228 KB: 115 472 B for <16,4,128>
     static constexpr size_t kSignBytes = (size_t)G * 4;
-    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + kCarryBytes + kSignBytes + 16;
+    static constexpr size_t kIdxBytes = (size_t)G * 4;  // channel index of every walked channel (direct: c0 + i; guard: list)
+    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + kCarryBytes + kSignBytes + kIdxBytes + 16;
 };
 
-template <int BS, int R, int NT, int CTAS, bool PF, int G = kFastGMax>
+// IND = false: grid (segments, channel groups), one work item per CTA. IND = true (dynamic-range guard of the STFT
+// mode): persistent 1-D grid, CTA i walks items i, i + gridDim.x, ... of a device-resident list; an item is <= 32
+// channels of one segment, named by index in the segment's selection list.
+template <int BS, int R, int NT, int CTAS, bool PF, bool IND, int G = kFastGMax>
 __global__ void __launch_bounds__(NT, CTAS)
-    demod_fast_kernel(DemodLaunch p, uint32_t ch_per_cta, uint32_t tiles_per_seg) {
+    demod_fast_kernel(DemodLaunch p, uint32_t ch_per_cta, uint32_t tiles_per_seg, FastIndirect ind) {
     using Cfg = FastCfg<BS, R, NT, G>;
     static_assert(32 % R == 0 && (R == 2 || R == 4), "R must be 2 or 4");
     static_assert(NT >= 32 && Cfg::kHaloT <= NT, "tile too small");
+    static_assert(Cfg::kTile == (int)kFastTile, "segment geometry is part of the launch interface");
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* xs = smem;
     float2* E = reinterpret_cast<float2*>(smem + Cfg::kXBytes);
@@ -216,26 +221,41 @@ __global__ void __launch_bounds__(NT, CTAS)
     float2* carry_s = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes);
     float* sign_s = reinterpret_cast<float*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes +
                                              Cfg::kCarryBytes);
+    uint32_t* cidx_s = reinterpret_cast<uint32_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes +
+                                                   Cfg::kCarryBytes + Cfg::kSignBytes);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes +
-                                                Cfg::kCarryBytes + Cfg::kSignBytes);
+                                                Cfg::kCarryBytes + Cfg::kSignBytes + Cfg::kIdxBytes);
 
     const int t = threadIdx.x;
-    const uint32_t c0 = blockIdx.y * ch_per_cta;
-    const uint32_t nch = min(ch_per_cta, p.n_channels - c0);
-    const float2* const* __restrict__ phase_g = p.phase + c0;  // per-channel phase-table pointers (L1-resident)
-    // segment: outputs [seg_b0, seg_b1); its first tile starts 32 blocks early (overlap, no output there)
-    const int64_t seg_out = (int64_t)tiles_per_seg * Cfg::kTile - 32;
-    const int64_t seg_b0 = (int64_t)p.b0 + (int64_t)blockIdx.x * seg_out;
-    const int64_t seg_b1 = min(seg_b0 + seg_out, (int64_t)p.b1);
-
     const uint32_t bar_a = smem_u32(bar);
     if (t == 0) {
         mbar_init(bar_a, 1);
         fence_mbar_init();
     }
+    uint32_t n_wait = 0;  // mbarrier phases consumed so far (one per staged tile)
+    const uint32_t n_items = IND ? __ldg(ind.n_items) : 1u;
+    for (uint32_t item = IND ? blockIdx.x : 0u; item < n_items; item += IND ? gridDim.x : 1u) {
+    uint32_t seg, nch;
+    if constexpr (IND) {
+        const GuardItem it = ind.items[item];
+        seg = it.seg;
+        nch = it.count;
+        __syncthreads();  // (first item: the mbarrier init; later items: nothing reads the staged tables any more)
+        if ((uint32_t)t < nch) cidx_s[t] = __ldg(ind.sel + (size_t)seg * ind.sel_stride + it.first + t);
+    } else {
+        seg = blockIdx.x;
+        const uint32_t c0 = blockIdx.y * ch_per_cta;
+        nch = min(ch_per_cta, p.n_channels - c0);
+        if ((uint32_t)t < nch) cidx_s[t] = c0 + t;
+    }
+    // segment: outputs [seg_b0, seg_b1); its first tile starts 32 blocks early (overlap, no output there)
+    const int64_t seg_out = (int64_t)tiles_per_seg * Cfg::kTile - 32;
+    const int64_t seg_b0 = (int64_t)p.b0 + (int64_t)seg * seg_out;
+    const int64_t seg_b1 = min(seg_b0 + seg_out, (int64_t)p.b1);
+    __syncthreads();
     for (uint32_t i = t; i < nch * (BS / 2); i += NT)
-        tone_s[i] = reinterpret_cast<const float4*>(p.tone)[(size_t)c0 * (BS / 2) + i];
-    for (uint32_t i = t; i < nch; i += NT) sign_s[i] = p.sign[c0 + i];
+        tone_s[i] = reinterpret_cast<const float4*>(p.tone)[(size_t)cidx_s[i / (BS / 2)] * (BS / 2) + i % (BS / 2)];
+    for (uint32_t i = t; i < nch; i += NT) sign_s[i] = p.sign[cidx_s[i]];
     __syncthreads();
 
     const float4* __restrict__ xrow = reinterpret_cast<const float4*>(xs + (size_t)t * Cfg::kRowStride);
@@ -269,11 +289,12 @@ __global__ void __launch_bounds__(NT, CTAS)
 #pragma unroll
         for (int i = 0; i < R / 2; ++i) Pnext[i] = make_float4(1.f, 0.f, 1.f, 0.f);
         if (row_valid) {
-            const float4* pp = reinterpret_cast<const float4*>(phase_g[0] + kbase);
+            const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[0]] + kbase);
 #pragma unroll
             for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
         }
-        mbar_wait(bar_a, tile & 1u);
+        mbar_wait(bar_a, n_wait & 1u);
+        ++n_wait;
 
         // IQ samples and tone entries of the NEXT block to be mixed live in registers: they are dead as soon
         // as the block is mixed, so the next block's are fetched right then and their LDS latency hides under
@@ -288,7 +309,7 @@ __global__ void __launch_bounds__(NT, CTAS)
         }
 
         for (uint32_t ci = 0; ci < nch; ++ci) {
-            const uint32_t c = c0 + ci;
+            const uint32_t c = cidx_s[ci];
             // acc[i] = partial sum for output offset (blocks done so far) + i
             float2 acc[32];
             float2 own[R];  // finished-as-far-as-I-am-concerned sums of my own R outputs
@@ -304,7 +325,7 @@ __global__ void __launch_bounds__(NT, CTAS)
 #pragma unroll
                 for (int i = 0; i < R / 2; ++i) Pcur[i] = Pnext[i];
                 if (ci + 1 < nch) {
-                    const float4* pp = reinterpret_cast<const float4*>(phase_g[ci + 1] + kbase);
+                    const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[ci + 1]] + kbase);
 #pragma unroll
                     for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
                 }
@@ -420,6 +441,7 @@ __global__ void __launch_bounds__(NT, CTAS)
             __syncthreads();  // E/O are rewritten by the next channel, the IQ rows by the next tile
         }
     }
+    }  // items
 }
 
 // Opt the kernel in to its dynamic shared memory size (per device: function attributes are per context) and
@@ -454,8 +476,8 @@ static cudaError_t prepare_kernel(const void* kern, int smem_bytes, int* sms) {
 // wave of CTAs. Cost model in block units, minimised over L.
 static uint32_t choose_tiles_per_seg(uint32_t n_out, uint32_t tile, uint32_t ch_groups, uint32_t slots,
                                      uint32_t overlap = 32) {
-    // CWSL_TILES_PER_SEG=<n> pins the segment length (tests and compute-sanitizer runs use it to force the
-    // cross-tile carry path on small inputs)
+    // (EXACT mode only: its result is bit-identical however it is segmented.) CWSL_TILES_PER_SEG=<n> pins the
+    // segment length (tests and compute-sanitizer runs use it to force the cross-tile carry path on small inputs)
     static const uint32_t forced = [] {
         const char* e = std::getenv("CWSL_TILES_PER_SEG");
         return e ? (uint32_t)std::strtoul(e, nullptr, 10) : 0u;
@@ -666,19 +688,37 @@ cudaError_t launch_demod_exact_gather(const DemodLaunch& p, cudaStream_t s) {
 }
 
 template <int BS, int R, int NT, int CTAS, bool PF, int G = kFastGMax>
-static cudaError_t launch_fast_t(const DemodLaunch& p, cudaStream_t s) {
+static cudaError_t launch_fast_t(const DemodLaunch& p, uint32_t l, const FastIndirect& ind, cudaStream_t s) {
     using Cfg = FastCfg<BS, R, NT, G>;
-    auto kern = demod_fast_kernel<BS, R, NT, CTAS, PF, G>;
+    const uint32_t seg_out = l * Cfg::kTile - 32;
+    if (p.b0 % seg_out != 0) return cudaErrorInvalidValue;  // segments sit at fixed slot-relative positions
     int sms = 0;
+    if (ind.items) {
+        auto kern = demod_fast_kernel<BS, R, NT, CTAS, PF, true, G>;
+        if (cudaError_t e = prepare_kernel((const void*)kern, (int)Cfg::kSmem, &sms); e != cudaSuccess) return e;
+        kern<<<(uint32_t)sms * CTAS, NT, Cfg::kSmem, s>>>(p, 0u, l, ind);
+        return cudaGetLastError();
+    }
+    auto kern = demod_fast_kernel<BS, R, NT, CTAS, PF, false, G>;
     if (cudaError_t e = prepare_kernel((const void*)kern, (int)Cfg::kSmem, &sms); e != cudaSuccess) return e;
     const uint32_t n_out = p.b1 - p.b0;
     const uint32_t g = p.n_channels < (uint32_t)G ? p.n_channels : (uint32_t)G;
     const uint32_t groups = (p.n_channels + g - 1) / g;
-    const uint32_t l = choose_tiles_per_seg(n_out, Cfg::kTile, groups, (uint32_t)sms * CTAS);
-    const uint32_t seg_out = l * Cfg::kTile - 32;
     dim3 grid((n_out + seg_out - 1) / seg_out, groups);
-    kern<<<grid, NT, Cfg::kSmem, s>>>(p, g, l);
+    kern<<<grid, NT, Cfg::kSmem, s>>>(p, g, l, ind);
     return cudaGetLastError();
+}
+
+// Tiles per segment of the FAST-tolerance modes: a function of the slot group's size only, so that the segmentation
+// (hence every rounding) of a slot does not depend on how its IQ was pushed. CWSL_TILES_PER_SEG=<n> pins it (tests
+// and compute-sanitizer runs use that to force the cross-tile carry path on small inputs).
+uint32_t fast_tiles_per_seg(uint32_t n_group_channels) {
+    static const uint32_t forced = [] {
+        const char* e = std::getenv("CWSL_TILES_PER_SEG");
+        return e ? (uint32_t)std::strtoul(e, nullptr, 10) : 0u;
+    }();
+    if (forced > 0) return forced;
+    return n_group_channels >= kSegLargeGroup ? kSegLargeGroupTiles : kSegSmallGroupTiles;
 }
 
 cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
@@ -704,8 +744,9 @@ cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
     }
 }
 
-cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s) {
+cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, const FastIndirect& ind, cudaStream_t s) {
     if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
+    if (tiles_per_seg == 0) return cudaErrorInvalidValue;
     // CWSL_FAST_PREFETCH=1: keep the next block's samples/tones in registers (fetched right after the mix).
     // Measured SLOWER on B200 (563.7 vs 573.4 G ch-samples/s: the 64 extra live registers cost more than the
     // shared-memory latency they hide); kept as a documented negative result.
@@ -717,9 +758,10 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s) {
     // measured 506 vs 574 G ch-samples/s on B200, so the shape below stays.)
     switch (p.block_size) {
         case 16:
-            return pf ? launch_fast_t<16, 4, 128, 2, true>(p, s) : launch_fast_t<16, 4, 128, 2, false>(p, s);
-        case 8: return launch_fast_t<8, 4, 128, 2, false>(p, s);
-        case 4: return launch_fast_t<4, 4, 128, 2, false>(p, s);
+            return pf ? launch_fast_t<16, 4, 128, 2, true>(p, tiles_per_seg, ind, s)
+                      : launch_fast_t<16, 4, 128, 2, false>(p, tiles_per_seg, ind, s);
+        case 8: return launch_fast_t<8, 4, 128, 2, false>(p, tiles_per_seg, ind, s);
+        case 4: return launch_fast_t<4, 4, 128, 2, false>(p, tiles_per_seg, ind, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -796,13 +838,35 @@ cudaError_t launch_quantise(const QuantLaunch& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-__global__ void clear_u32_kernel(unsigned* p, uint32_t n) {
+__global__ void clear_u32_kernel(unsigned* p, uint32_t n, unsigned long long* counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0u;
+    if (counters && i == 0) {  // guard counters of the slot that just ended -> "last finished slot"
+        counters[2] = counters[0];
+        counters[3] = counters[1];
+        counters[0] = counters[1] = 0ull;
+    }
 }
-cudaError_t launch_clear_u32(unsigned* p, uint32_t n, cudaStream_t s) {
+cudaError_t launch_clear_u32(unsigned* p, uint32_t n, unsigned long long* counters, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    clear_u32_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n);
+    clear_u32_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, counters);
+    return cudaGetLastError();
+}
+
+// P_c[spacing * a] of every channel's exact phase table, [anchor][channel] (coalesced for the STFT consumers)
+__global__ void phase_anchor_kernel(const float2* const* __restrict__ phase, float2* __restrict__ anchors, uint32_t n_channels,
+                                    uint64_t total, uint32_t spacing) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint64_t a = i / n_channels;
+    const uint32_t c = (uint32_t)(i - a * n_channels);
+    anchors[i] = __ldg(phase[c] + a * spacing);
+}
+cudaError_t launch_phase_anchors(const float2* const* phase, float2* anchors, uint32_t n_channels, uint32_t n_anchor,
+                                 uint32_t spacing, cudaStream_t s) {
+    const uint64_t total = (uint64_t)n_channels * n_anchor;
+    if (total == 0) return cudaSuccess;
+    phase_anchor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(phase, anchors, n_channels, total, spacing);
     return cudaGetLastError();
 }
 

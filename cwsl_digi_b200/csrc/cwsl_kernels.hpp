@@ -41,10 +41,37 @@ struct QuantLaunch {
     float* max_out = nullptr;      // [n_channels] maxVal of prepareAudio
 };
 
+// Time segmentation of the FAST-tolerance kernels. A slot is cut into SEGMENTS of kFastTile*L - 32 outputs at fixed
+// slot-relative positions; L depends on the size of the slot group only (never on how the IQ was pushed), launches of
+// the FAST / STFT modes start on segment boundaries, and everything a segment computes is a function of the slot's
+// IQ and the slot-relative block index alone -> equal IQ gives equal bytes however it is chunked.
+constexpr uint32_t kFastTile = 512;            // SSBD blocks per tile of demod_fast_kernel (128 threads x 4 blocks)
+constexpr uint32_t kSegLargeGroupTiles = 3;    // groups of >= kSegLargeGroup channels: 1504 outputs per segment
+constexpr uint32_t kSegSmallGroupTiles = 1;    // smaller groups: 480 outputs per segment (more CTAs per launch)
+constexpr uint32_t kSegLargeGroup = 64;
+uint32_t fast_tiles_per_seg(uint32_t n_group_channels);  // CWSL_TILES_PER_SEG overrides (tests)
+inline uint32_t fast_seg_blocks(uint32_t tiles_per_seg) { return tiles_per_seg * kFastTile - 32; }
+
+// Work item of the indirect FAST launch (dynamic-range guard of the STFT mode): <= 32 channels of one segment.
+struct GuardItem {
+    uint32_t seg;    // segment index inside the launch
+    uint32_t first;  // first entry of the segment's selection list
+    uint32_t count;  // 1..32
+    uint32_t pad;
+};
+// Channels that a FAST launch takes from device-resident lists instead of the grid (nullptr members = direct launch)
+struct FastIndirect {
+    const GuardItem* items = nullptr;
+    const unsigned* n_items = nullptr;  // device counter written by guard_select_kernel
+    const uint32_t* sel = nullptr;      // [n_seg][sel_stride] channel indices, ascending per segment
+    uint32_t sel_stride = 0;
+};
+
 // Extra inputs of the STFT channelizer kernel (cwsl_chan.cu); tables from cwsl_tables.hpp chan_*.
 constexpr int kChanTaps = 8;                   // stencil bins per channel: Kaiser-Bessel kernel of width 7 on an even-aligned stencil
 constexpr int kChanKernelWidth = 7;
 constexpr uint32_t kChanMaxChannels = 1024;    // per launch (each interpolation thread keeps <= 4 channels in registers)
+constexpr uint32_t kChanAnchorHops = 128;      // the exact phase recurrence is re-read every 128 hops (slot-relative)
 struct alignas(16) ChanConst {   // per-channel constants, four 16-byte loads
     int q0;           // first grid bin of the interpolation stencil, even (bins are taken mod 1024)
     float sign;       // +1 USB / -1 LSB
@@ -58,6 +85,30 @@ struct ChanLaunch {
     const float2* twiddle = nullptr;  // [32][32] W1024^(j2*q1) * i^q1 at [q1*32 + j2]
     const ChanConst* consts = nullptr;  // [n_channels]
     int taps = kChanTaps;
+    // P_c[128 a] of the exact float recurrence, [anchor][channel] so that a warp reads 256 contiguous bytes
+    const float2* anchors = nullptr;
+    uint32_t anchor_stride = 0;       // channels per anchor row (the whole slot group)
+    // Dynamic-range guard statistics per (segment of this launch, channel); seg_blocks == 0: guard off, max|x| goes
+    // straight to DemodLaunch::maxbits
+    uint32_t seg_blocks = 0;
+    unsigned* seg_max = nullptr;      // [n_seg][stat_stride] bit pattern of max|y| over the segment
+    unsigned* seg_energy = nullptr;   // [n_seg][stat_stride] sum over octets of min(2^20, sum_8 y^2 * seg_scale[seg])
+    const float* seg_scale = nullptr; // [n_seg] 128 / (T^2 * mean|x|^2 of the segment's IQ)
+    uint32_t stat_stride = 0;
+};
+// Guard launch parameters (cwsl_guard.cu)
+struct GuardLaunch {
+    uint32_t seg_blocks = 0;          // W
+    float t2 = 0.0f;                  // T^2: a channel segment keeps the STFT result iff mean y^2 >= T^2 * mean |x|^2
+    float* seg_scale = nullptr;       // [n_seg]
+    unsigned* seg_max = nullptr;
+    unsigned* seg_energy = nullptr;
+    uint32_t stat_stride = 0;
+    uint32_t* sel = nullptr;          // [n_seg][sel_stride]
+    uint32_t sel_stride = 0;
+    GuardItem* items = nullptr;       // [n_seg * ceil(C/32)]
+    unsigned* n_items = nullptr;
+    unsigned long long* counters = nullptr;  // [0] channel-segments decided, [1] of those re-run by the FAST kernel (this slot)
 };
 
 // Upload the normalised low-pass taps for one block size into constant memory.
@@ -71,11 +122,20 @@ cudaError_t launch_phase_tables(const float2* phase_inc /*[n]*/, float2* const* 
 
 cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s);         // tiled, production
 cudaError_t launch_demod_exact_gather(const DemodLaunch& p, cudaStream_t s);  // one thread per output, cross-check
-cudaError_t launch_demod_fast(const DemodLaunch& p, cudaStream_t s);
-// STFT channelizer (192 kHz receivers, <= kChanMaxChannels channels per launch)
+// FAST: p.b0 must be a multiple of fast_seg_blocks(tiles_per_seg) (segments sit at fixed slot-relative positions).
+// ind.items != nullptr: the channels come from the guard's device-resident work list (persistent grid).
+cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, const FastIndirect& ind, cudaStream_t s);
+// STFT channelizer (<= kChanMaxChannels channels per launch); p.b0 must be a multiple of 32
 cudaError_t launch_demod_chan(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s);
+// P_c[spacing * a] gathered from the full phase tables into [n_anchor][n_channels]
+cudaError_t launch_phase_anchors(const float2* const* phase, float2* anchors, uint32_t n_channels, uint32_t n_anchor,
+                                 uint32_t spacing, cudaStream_t s);
+// Guard: per-segment band power -> seg_scale (before the channelizer), selection + max merge (after it)
+cudaError_t launch_guard_band_power(const DemodLaunch& p, const GuardLaunch& g, cudaStream_t s);
+cudaError_t launch_guard_select(const DemodLaunch& p, const GuardLaunch& g, cudaStream_t s);
 cudaError_t launch_quantise(const QuantLaunch& p, cudaStream_t s);
-cudaError_t launch_clear_u32(unsigned* p, uint32_t n, cudaStream_t s);
+// p[0..n) = 0; if counters != nullptr: counters[2..3] = counters[0..1] (last finished slot), counters[0..1] = 0
+cudaError_t launch_clear_u32(unsigned* p, uint32_t n, unsigned long long* counters, cudaStream_t s);
 
 // FP32 pipe microbenchmark (TFLOP/s).
 cudaError_t measure_fp32_peak(float* ffma_tflops, float* ffma2_tflops);

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CWSL_B200_ABI_VERSION 1
+#define CWSL_B200_ABI_VERSION 2
 
 #define CWSL_OK 0
 #define CWSL_ERR_INVALID (-1)  /* bad argument; where the reference throws std::invalid_argument
@@ -39,13 +39,20 @@ extern "C" {
  *        with strict IEEE flags (oracle/_ref).
  * FAST:  same tables and the same float phase recurrence, FMA-contracted mix and FIR
  *        (packed fma.rn.f32x2) -> <= 1 int16 LSB, residual >= 90 dB below signal.
- * STFT:  same tolerance class as FAST, for receivers with many channels: per output sample (hop of one SSBD block)
- *        ONE FFT of the windowed last FiltOrder IQ samples on a 2*FiltOrder grid (1024 / 512 / 256 bins at
- *        192 / 96 / 48 kHz) is shared by every channel of the slot group, and each channel reads its NCO
- *        frequency off that grid (8-bin Kaiser-Bessel interpolation) and applies the reference's own float
- *        phase recurrence. Used for groups of >= 64 channels (CWSL_STFT_MIN_CHANNELS; the measured break-even with the FAST kernel); smaller groups run the
- *        FAST kernel. <= 1 int16 LSB, residual <= -120 dB on the benchmark input;
- *        dynamic range between channels is that of a float32 FFT (~ -140 dB of the strongest signal). */
+ * STFT:  for receivers with many channels: per output sample (hop of one SSBD block) ONE FFT of the windowed last
+ *        FiltOrder IQ samples on a 2*FiltOrder grid (1024 / 512 / 256 bins at 192 / 96 / 48 kHz) is shared by every
+ *        channel of the slot group; each channel reads its NCO frequency off that grid (8-bin Kaiser-Bessel
+ *        interpolation) and applies the reference's own float phase recurrence. Used for groups of >= 64 channels
+ *        (CWSL_STFT_MIN_CHANNELS; the measured break-even with the FAST kernel); smaller groups run the FAST kernel.
+ *        Contract: <= 1 int16 LSB, residual >= 90 dB below the channel's signal -- the same bars as FAST. The FFT's
+ *        own error is NOT relative to the channel: it is the rounding noise of a float32 FFT, 1.7e-7 (-135 dB) of
+ *        the rms of the whole band. The bars are kept by a dynamic-range guard: per segment of 1504 output samples,
+ *        a channel whose mean power lies more than 42 dB (cwsl_rx_set_stft_guard) under the band's is recomputed by
+ *        the FAST kernel on the device before the slot is normalised, so every sample handed on is either an FFT
+ *        sample >= 93 dB above the FFT floor or a FAST sample.
+ * FAST and STFT results are functions of the slot's IQ alone: segment and anchor positions are fixed in
+ * slot-relative coordinates, so equal IQ gives equal bytes however it was pushed (cwsl_rx_push_iq chunking,
+ * cwsl_rx_process calls). For that the two modes demodulate whole segments only until the slot edge. */
 #define CWSL_MODE_EXACT 0
 #define CWSL_MODE_FAST 1
 #define CWSL_MODE_STFT 2
@@ -95,12 +102,19 @@ size_t cwsl_accepted_blocks(size_t n_iq_blocks, uint32_t iq_len, uint32_t sample
  * iq_len must be a multiple of SSBD::GetInSize() (the reference silently over-reads otherwise,
  * source/Instance.cpp:273). ring_seconds sizes the device-resident IQ ring (the reference keeps
  * ~3 s of blocks on the host, source/Receiver.hpp:132); 0 = size it for the longest slot of the
- * groups added before the first push. Returns NULL on failure (see cwsl_last_error). */
+ * groups added before the first push. It is a minimum: the ring always holds at least two segments
+ * (about 0.26 s). Returns NULL on failure (see cwsl_last_error). */
 cwsl_rx_t* cwsl_rx_create(int device, uint32_t sample_rate, uint32_t iq_len, double ring_seconds);
 void cwsl_rx_destroy(cwsl_rx_t* rx);
 
-/* EXACT or FAST (default FAST). */
+/* CWSL_MODE_EXACT, CWSL_MODE_FAST (default) or CWSL_MODE_STFT. Takes effect at each slot group's next slot edge (the
+ * mode of a slot is latched at its first demodulation), so a slot is never a mixture of two modes. */
 int cwsl_rx_set_mode(cwsl_rx_t* rx, int mode);
+
+/* Threshold of the STFT mode's dynamic-range guard, in dB below the mean power of the band: channel segments whose
+ * mean power is lower are recomputed in the direct form (see CWSL_MODE_STFT). Default 42 (CWSL_STFT_GUARD_DB);
+ * 0 switches the guard off (diagnostics: the raw FFT channelizer). */
+int cwsl_rx_set_stft_guard(cwsl_rx_t* rx, double db_below_band_power);
 
 /* A slot group = the decoders that share one SyncPredicate, i.e. one mode/period
  * (source/CWSL_DIGI_Types.hpp:65-145, source/CWSL_DIGI.cpp:134). period_s as getRXPeriod()
@@ -113,8 +127,18 @@ int cwsl_rx_add_group(cwsl_rx_t* rx, double period_s);
  * (source/Instance.cpp:320-329, source/CWSL_DIGI.cpp:952-978). Builds the reference's tables on
  * the host and the float phase sequence phase_inc^k (source/SSBD.hpp:174) on the device.
  * Returns the channel index inside the group (>= 0) or a negative error; CWSL_ERR_INVALID for
- * tunings SSBD::Tune rejects (source/SSBD.hpp:100-103). Must precede the first push. */
+ * tunings SSBD::Tune rejects (source/SSBD.hpp:100-103).
+ * On a receiver that is already running (a decoder restarted or moved to this band by the main loop,
+ * source/CWSL_DIGI.cpp:1217-1226 -> setupDecoder) the channel joins at the group's next slot edge -- immediately if
+ * no IQ of an open slot is pending; the returned index is the one it will have then (channels keep their order;
+ * a removal pending for the same edge moves it down). A cwsl_rx_end_slot that has
+ * such a change pending must take its result to the host (out_i16 != NULL): the device buffers are replaced. */
 int cwsl_rx_add_channel(cwsl_rx_t* rx, int group, int32_t demod_freq_hz, int is_usb, float scale);
+
+/* Remove a decoder channel (Instance::terminate, source/Instance.cpp:100-119). Before the first push: at once.
+ * On a running receiver: at the group's next slot edge (immediately between slots); channels behind it move down
+ * by one index then. A group cannot lose its last channel (destroy the receiver instead). */
+int cwsl_rx_remove_channel(cwsl_rx_t* rx, int group, int channel);
 
 int cwsl_rx_num_groups(const cwsl_rx_t* rx);
 int cwsl_rx_num_channels(const cwsl_rx_t* rx, int group);
@@ -138,9 +162,10 @@ int cwsl_rx_push_iq_device(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks);
  * Replaces any ring contents; nothing is copied. Same stream semantics as cwsl_rx_push_iq_device. */
 int cwsl_rx_bind_device_iq(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks);
 
-/* Demodulate everything pushed so far for `group` (or all groups if group < 0) without ending
+/* Demodulate what has been pushed so far for `group` (or all groups if group < 0) without ending
  * the slot: the streaming counterpart of the per-block Iterate loop, source/Instance.cpp:273-276.
- * Asynchronous. */
+ * EXACT mode: everything; FAST / STFT: all complete segments (1504 output samples for groups of >= 64 channels,
+ * 480 for smaller ones), the rest waits in the ring for the next call or the slot edge. Asynchronous. */
 int cwsl_rx_process(cwsl_rx_t* rx, int group);
 
 /* Slot edge for `group` = the SyncPredicate firing (source/Instance.cpp:203-253): finishes the
@@ -206,6 +231,15 @@ int cwsl_rx_enable_timing(cwsl_rx_t* rx, int on);
  * Synchronises the stream. Any pointer may be NULL. */
 int cwsl_rx_kernel_times(cwsl_rx_t* rx, float* demod_ms, float* quant_ms, int* demod_launches,
                          int* quant_launches);
+
+/* ms[5] = {demodulation total, normalise+quantise total, main demodulator kernel(s) only, STFT guard prologue
+ * (band power), STFT guard epilogue (selection + direct-form redo)}, launches[2] = {demodulation passes,
+ * quantise passes} since the last call; otherwise like cwsl_rx_kernel_times. */
+int cwsl_rx_kernel_times_ex(cwsl_rx_t* rx, float ms[5], int launches[2]);
+
+/* STFT dynamic-range guard, last finished slot of `group`: channel segments decided, and how many of those were
+ * recomputed by the FAST kernel. Synchronous. */
+int cwsl_rx_guard_stats(cwsl_rx_t* rx, int group, uint64_t* decided, uint64_t* redone);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* FP32 FMA-pipe peak of `device`, measured with a register-resident FFMA / packed FFMA2

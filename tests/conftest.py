@@ -8,7 +8,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-# CWSL_MODE_STFT normally leaves groups of < 48 channels to the FAST kernel; the parity tests want the channelizer
+# CWSL_MODE_STFT normally leaves groups of < 64 channels to the FAST kernel; the parity tests want the channelizer
 # kernel itself on their small channel sets (the knob is read once, at the first demodulation of the process)
 os.environ.setdefault("CWSL_STFT_MIN_CHANNELS", "1")
 
