@@ -20,6 +20,7 @@ SYMBOLS = [
     "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_wait_output", "cwsl_rx_stream", "cwsl_rx_set_stream", "cwsl_rx_enable_timing",
     "cwsl_rx_kernel_times", "cwsl_measure_fp32_peak", "cwsl_host_alloc", "cwsl_host_free",
     "cwsl_rx_set_stft_guard", "cwsl_rx_remove_channel", "cwsl_rx_kernel_times_ex", "cwsl_rx_guard_stats",
+    "cwsl_rx_push_fence", "cwsl_rx_wait_fence",
 ]
 
 
@@ -99,6 +100,8 @@ def lib() -> C.CDLL:
     L.cwsl_rx_remove_channel.argtypes = [vp, C.c_int, C.c_int]
     L.cwsl_rx_kernel_times_ex.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.cwsl_rx_guard_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.cwsl_rx_push_fence.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.cwsl_rx_wait_fence.argtypes = [vp, C.c_uint64]
     L.cwsl_host_alloc.restype = vp
     L.cwsl_host_alloc.argtypes = [sz]
     L.cwsl_host_free.restype = None
@@ -257,6 +260,14 @@ class Receiver:
 
     def push_iq_device(self, dptr: int, n_blocks: int) -> None:
         _check(self._L.cwsl_rx_push_iq_device(self._h, dptr, n_blocks))
+
+    def push_fence(self) -> int:
+        tok = C.c_uint64()
+        _check(self._L.cwsl_rx_push_fence(self._h, C.byref(tok)))
+        return tok.value
+
+    def wait_fence(self, token: int) -> None:
+        _check(self._L.cwsl_rx_wait_fence(self._h, token))
 
     def bind_device_iq(self, dptr: int, n_blocks: int) -> None:
         _check(self._L.cwsl_rx_bind_device_iq(self._h, dptr, n_blocks))

@@ -165,6 +165,11 @@ struct cwsl_rx {
     bool bound = false;
     bool committed = false;
     std::vector<Group> groups;
+    // push fences: events recorded on `stream` behind pushes, so a caller that stages IQ in a ring of pinned
+    // buffers can wait for exactly the copy that last read the buffer it wants to refill
+    static constexpr uint64_t kFences = 64;
+    cudaEvent_t fence_ev[kFences] = {};
+    uint64_t fence_next = 1;  // token of the next fence; token t lives in fence_ev[t % kFences]
     double guard_db = 0;  // STFT dynamic-range guard threshold (dB below the band's mean power); <= 0: off
     // timing
     bool timing = false;
@@ -445,7 +450,7 @@ int ensure_stft(cwsl_rx* rx, Group& g) {
         std::lock_guard<std::mutex> lk(g_mu);
         AnchorEntry& e = g_anchor_cache[g.phase_keys];
         if (!e.table) {
-            const uint32_t n_anchor = (uint32_t)(g.af_size / cwsl::kChanAnchorHops + 2);
+            const uint32_t n_anchor = (uint32_t)(g.af_size / cwsl::kChanAnchorHops + 1);  // 128 a <= af_size < table length
             float2* tab = nullptr;
             cudaError_t err = commit_nosync() ? cudaSuccess : cudaDeviceSynchronize();
             if (err == cudaSuccess) err = cudaMalloc(&tab, (size_t)n_anchor * C * sizeof(float2));
@@ -535,13 +540,14 @@ uint32_t stft_min_channels() {
     return v;
 }
 
-// Default threshold of the STFT dynamic-range guard, dB below the band's mean power (cwsl_guard.cu); the measured
-// float32-FFT floor is 1.7e-7 of the band's rms (-135 dB), 90 dB above it is -45 dB, 3 dB of margin.
+// Default threshold of the STFT dynamic-range guard, dB below the band's mean power (cwsl_guard.cu). Measured float32
+// FFT floor: at worst 5.8e-7 of the band's rms (-124.7 dB; single dominant carrier), typically 1.9e-7; 90 dB above
+// the worst case is -34.7 dB, the default leaves 2.7 dB of margin. (The stress sweep's channels sit at -18 ... -24 dB.)
 // CWSL_STFT_GUARD_DB overrides (0 = guard off).
 double default_guard_db() {
     static const double v = [] {
         const char* e = std::getenv("CWSL_STFT_GUARD_DB");
-        return e ? std::atof(e) : 42.0;
+        return e ? std::atof(e) : 32.0;
     }();
     return v;
 }
@@ -874,6 +880,8 @@ void cwsl_rx_destroy(cwsl_rx_t* rx) {
         cudaEventDestroy(pr.second);
     }
     for (auto e : rx->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : rx->fence_ev)
+        if (e) cudaEventDestroy(e);
     if (rx->stream && rx->own_stream) cudaStreamDestroy(rx->stream);
     if (rx->copy_stream) cudaStreamDestroy(rx->copy_stream);
     if (rx->ev_out_ready) cudaEventDestroy(rx->ev_out_ready);
@@ -1055,6 +1063,27 @@ int cwsl_rx_push_iq(cwsl_rx_t* rx, const float* iq, size_t n_blocks) {
 
 int cwsl_rx_push_iq_device(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks) {
     return push_common(rx, d_iq, n_blocks, cudaMemcpyDeviceToDevice);
+}
+
+int cwsl_rx_push_fence(cwsl_rx_t* rx, uint64_t* token) {
+    if (!rx || !token) return fail(CWSL_ERR_INVALID, "bad arguments");
+    DeviceGuard dg(rx->device);
+    if (!dg.ok) return fail(CWSL_ERR_CUDA, "cudaSetDevice(%d) failed", rx->device);
+    cudaEvent_t& e = rx->fence_ev[rx->fence_next % cwsl_rx::kFences];
+    if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventRecord(e, rx->stream));  // (re-recording a slot: its old token is kFences fences older, see wait)
+    *token = rx->fence_next++;
+    return CWSL_OK;
+}
+
+int cwsl_rx_wait_fence(cwsl_rx_t* rx, uint64_t token) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    if (token == 0 || token >= rx->fence_next) return fail(CWSL_ERR_INVALID, "unknown fence %llu", (unsigned long long)token);
+    DeviceGuard dg(rx->device);
+    // A slot that has been re-recorded since holds a LATER fence of the same stream: waiting for that one is
+    // sufficient (stream order), merely longer than necessary.
+    CK(cudaEventSynchronize(rx->fence_ev[token % cwsl_rx::kFences]));
+    return CWSL_OK;
 }
 
 int cwsl_rx_bind_device_iq(cwsl_rx_t* rx, const float* d_iq, size_t n_blocks) {

@@ -198,9 +198,11 @@ struct FastCfg {
     static constexpr size_t kToneBytes = (size_t)G * BS * 8;
     static constexpr size_t kCarryBytes = (size_t)G * 31 * 8;
     // 2 CTAs/SM need 2*(kSmem + 1 KB reserved) <= 228 KB: 115 472 B for <16,4,128>
-    static constexpr size_t kSignBytes = (size_t)G * 4;
-    static constexpr size_t kIdxBytes = (size_t)G * 4;  // channel index of every walked channel (direct: c0 + i; guard: list)
-    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + kCarryBytes + kSignBytes + kIdxBytes + 16;
+    // channel index of every walked channel (direct: c0 + i; guard: from the selection list), sideband in bit 31.
+    // (Not one byte more than this: 2 CTAs/SM is the whole point of the shape, and 128 B more lose the second CTA --
+    // measured 6.06 instead of 4.85 ms per 1024-channel FT8 slot.)
+    static constexpr size_t kIdxBytes = (size_t)G * 4;
+    static constexpr size_t kSmem = kXBytes + kEBytes + kOBytes + kToneBytes + kCarryBytes + kIdxBytes + 16;
 };
 
 // IND = false: grid (segments, channel groups), one work item per CTA. IND = true (dynamic-range guard of the STFT
@@ -219,12 +221,11 @@ __global__ void __launch_bounds__(NT, CTAS)
     float2* O = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kEBytes);
     float4* tone_s = reinterpret_cast<float4*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes);
     float2* carry_s = reinterpret_cast<float2*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes);
-    float* sign_s = reinterpret_cast<float*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes +
-                                             Cfg::kCarryBytes);
     uint32_t* cidx_s = reinterpret_cast<uint32_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes +
-                                                   Cfg::kCarryBytes + Cfg::kSignBytes);
+                                                   Cfg::kCarryBytes);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::kXBytes + Cfg::kEBytes + Cfg::kOBytes + Cfg::kToneBytes +
-                                                Cfg::kCarryBytes + Cfg::kSignBytes + Cfg::kIdxBytes);
+                                                Cfg::kCarryBytes + Cfg::kIdxBytes);
+    constexpr uint32_t kIdxMask = 0x7fffffffu;
 
     const int t = threadIdx.x;
     const uint32_t bar_a = smem_u32(bar);
@@ -241,12 +242,15 @@ __global__ void __launch_bounds__(NT, CTAS)
         seg = it.seg;
         nch = it.count;
         __syncthreads();  // (first item: the mbarrier init; later items: nothing reads the staged tables any more)
-        if ((uint32_t)t < nch) cidx_s[t] = __ldg(ind.sel + (size_t)seg * ind.sel_stride + it.first + t);
+        if ((uint32_t)t < nch) {
+            const uint32_t c = __ldg(ind.sel + (size_t)seg * ind.sel_stride + it.first + t);
+            cidx_s[t] = c | (p.sign[c] < 0.0f ? 0x80000000u : 0u);
+        }
     } else {
         seg = blockIdx.x;
         const uint32_t c0 = blockIdx.y * ch_per_cta;
         nch = min(ch_per_cta, p.n_channels - c0);
-        if ((uint32_t)t < nch) cidx_s[t] = c0 + t;
+        if ((uint32_t)t < nch) cidx_s[t] = (c0 + t) | (p.sign[c0 + t] < 0.0f ? 0x80000000u : 0u);
     }
     // segment: outputs [seg_b0, seg_b1); its first tile starts 32 blocks early (overlap, no output there)
     const int64_t seg_out = (int64_t)tiles_per_seg * Cfg::kTile - 32;
@@ -254,8 +258,7 @@ __global__ void __launch_bounds__(NT, CTAS)
     const int64_t seg_b1 = min(seg_b0 + seg_out, (int64_t)p.b1);
     __syncthreads();
     for (uint32_t i = t; i < nch * (BS / 2); i += NT)
-        tone_s[i] = reinterpret_cast<const float4*>(p.tone)[(size_t)cidx_s[i / (BS / 2)] * (BS / 2) + i % (BS / 2)];
-    for (uint32_t i = t; i < nch; i += NT) sign_s[i] = p.sign[cidx_s[i]];
+        tone_s[i] = reinterpret_cast<const float4*>(p.tone)[(size_t)(cidx_s[i / (BS / 2)] & kIdxMask) * (BS / 2) + i % (BS / 2)];
     __syncthreads();
 
     const float4* __restrict__ xrow = reinterpret_cast<const float4*>(xs + (size_t)t * Cfg::kRowStride);
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(NT, CTAS)
 #pragma unroll
         for (int i = 0; i < R / 2; ++i) Pnext[i] = make_float4(1.f, 0.f, 1.f, 0.f);
         if (row_valid) {
-            const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[0]] + kbase);
+            const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[0] & kIdxMask] + kbase);
 #pragma unroll
             for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
         }
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(NT, CTAS)
         }
 
         for (uint32_t ci = 0; ci < nch; ++ci) {
-            const uint32_t c = cidx_s[ci];
+            const uint32_t c_sb = cidx_s[ci], c = c_sb & kIdxMask;
             // acc[i] = partial sum for output offset (blocks done so far) + i
             float2 acc[32];
             float2 own[R];  // finished-as-far-as-I-am-concerned sums of my own R outputs
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(NT, CTAS)
 #pragma unroll
                 for (int i = 0; i < R / 2; ++i) Pcur[i] = Pnext[i];
                 if (ci + 1 < nch) {
-                    const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[ci + 1]] + kbase);
+                    const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[ci + 1] & kIdxMask] + kbase);
 #pragma unroll
                     for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
                 }
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(NT, CTAS)
             // ---- epilogue: Weaver select, float audio store, max|x| ----
             float lmax = 0.0f;
             if (writes) {
-                const float sign = sign_s[ci];
+                const float sign = (c_sb >> 31) ? -1.0f : 1.0f;
                 float o4[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j) {

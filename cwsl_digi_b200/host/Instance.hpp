@@ -52,7 +52,12 @@ public:
         status = InstanceStatus::RUNNING;
         return true;
     }
-    void terminate() { status = InstanceStatus::FINISHED; }
+    // source/Instance.cpp:100-119: stops the decoder. Its channel leaves the receiver's slot group at the next slot
+    // edge; the status turns FINISHED once it has (at once if the receiver is not running).
+    void terminate() {
+        if (status != InstanceStatus::RUNNING || !receiver || !receiver->removeInstance(this)) status = InstanceStatus::FINISHED;
+    }
+    void markFinished() { status = InstanceStatus::FINISHED; }
     std::string instanceLog() const { return "Instance " + std::to_string(id) + " "; }
 
     // set by Receiver::addInstance
@@ -77,11 +82,30 @@ private:
 };
 
 // ---- Receiver members that need the complete Instance type ------------------------------------------
+inline bool Receiver::attach(SlotGroup& g, Instance* inst) {
+    const int ch = cwsl_rx_add_channel(rx, g.id, inst->demodFreq(), USB, inst->audioScale());
+    if (ch < 0) return false;  // e.g. "Signal outside of band", source/SSBD.hpp:100-103
+    inst->group = g.id;
+    inst->channel = ch;
+    g.members.push_back(inst);
+    g.preds.push_back(inst->getPredicate());
+    instances.push_back(inst);
+    return true;
+}
+
 inline bool Receiver::addInstance(Instance* inst) {
-    if (!rx || status == ReceiverStatus::RUNNING) return false;
+    if (!rx) return false;
+    std::lock_guard<std::mutex> lk(mu);
     SlotGroup* g = nullptr;
     for (auto& sg : groups)
         if (sg.period == inst->getTRPeriod()) g = &sg;
+    if (status == ReceiverStatus::RUNNING) {
+        // The reader thread owns the GPU handle while it runs: validate here, join at the group's next slot edge.
+        if (!g) return false;
+        if (cwsl_build_tables(radioSR, inst->demodFreq(), USB, nullptr, nullptr, nullptr) != CWSL_OK) return false;
+        g->joining.push_back(inst);
+        return true;
+    }
     if (!g) {
         SlotGroup sg;
         sg.period = inst->getTRPeriod();
@@ -90,23 +114,93 @@ inline bool Receiver::addInstance(Instance* inst) {
         groups.push_back(std::move(sg));
         g = &groups.back();
     }
-    const int ch = cwsl_rx_add_channel(rx, g->id, inst->demodFreq(), USB, inst->audioScale());
-    if (ch < 0) return false;  // e.g. "Signal outside of band", source/SSBD.hpp:100-103
-    inst->group = g->id;
-    inst->channel = ch;
-    g->members.push_back(inst);
-    g->preds.push_back(inst->getPredicate());
-    instances.push_back(inst);
-    return true;
+    return attach(*g, inst);
+}
+
+inline bool Receiver::removeInstance(Instance* inst) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& g : groups) {
+        for (std::size_t m = 0; m < g.members.size(); ++m) {
+            if (g.members[m] != inst) continue;
+            if (status == ReceiverStatus::RUNNING) {
+                g.leaving.push_back(inst);
+                return true;  // finishes at the next slot edge
+            }
+            return false;     // not running: nothing to wait for, the caller marks itself FINISHED
+        }
+        for (std::size_t j = 0; j < g.joining.size(); ++j)
+            if (g.joining[j] == inst) {
+                g.joining.erase(g.joining.begin() + j);
+                return false;
+            }
+    }
+    return false;
+}
+
+// Slot edge of the group, right after cwsl_rx_end_slot: no IQ of the next slot has been pushed yet, so the GPU side
+// applies channel-set changes at once and both sides switch for the same slot.
+inline void Receiver::applyMembership(SlotGroup& g) {
+    std::vector<Instance*> joining, leaving;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        joining.swap(g.joining);
+        leaving.swap(g.leaving);
+    }
+    for (Instance* inst : leaving) {
+        std::size_t m = 0;
+        while (m < g.members.size() && g.members[m] != inst) ++m;
+        if (m == g.members.size()) continue;
+        if (g.members.size() == 1 && joining.empty()) {
+            // the GPU group keeps its last channel (a group cannot be empty); its audio is simply no longer handed on
+            screenPrinter->debug(receiverLog() + "last decoder of a slot group terminated; the group idles");
+            g.idle = true;
+        } else if (cwsl_rx_remove_channel(rx, g.id, static_cast<int>(m)) != CWSL_OK) {
+            screenPrinter->err(receiverLog() + std::string("remove decoder: ") + cwsl_last_error());
+            continue;
+        }
+        if (!g.idle) {
+            g.members.erase(g.members.begin() + m);
+            g.preds.erase(g.preds.begin() + m);
+            for (std::size_t k = m; k < g.members.size(); ++k) g.members[k]->channel = static_cast<int>(k);
+        }
+        for (std::size_t k = 0; k < instances.size(); ++k)
+            if (instances[k] == inst) {
+                instances.erase(instances.begin() + k);
+                break;
+            }
+        inst->markFinished();
+    }
+    for (Instance* inst : joining) {
+        if (g.idle) {  // the idling channel is replaced: add first, then drop the old one
+            Instance* old = g.members.empty() ? nullptr : g.members[0];
+            if (!attach(g, inst)) {
+                screenPrinter->err(receiverLog() + std::string("add decoder: ") + cwsl_last_error());
+                inst->markFinished();
+                continue;
+            }
+            if (old && cwsl_rx_remove_channel(rx, g.id, 0) == CWSL_OK) {
+                g.members.erase(g.members.begin());
+                g.preds.erase(g.preds.begin());
+                for (std::size_t k = 0; k < g.members.size(); ++k) g.members[k]->channel = static_cast<int>(k);
+            }
+            g.idle = false;
+            continue;
+        }
+        if (!attach(g, inst)) {
+            screenPrinter->err(receiverLog() + std::string("add decoder: ") + cwsl_last_error());
+            inst->markFinished();
+        }
+    }
 }
 
 inline void Receiver::finishSlot(SlotGroup& g) {
     // source/Instance.cpp:203-253 for every decoder of the group
     const std::uint64_t now = std::chrono::system_clock::now().time_since_epoch() / std::chrono::seconds(1);
     const std::size_t afs = cwsl_rx_group_af_size(rx, g.id);
-    if (g.audioElems != g.members.size() * afs) {  // pinned + managed: only the demodulated columns cross PCIe
+    const std::size_t rows = static_cast<std::size_t>(cwsl_rx_num_channels(rx, g.id));
+    if (g.audioElems != rows * afs) {  // pinned + managed: only the demodulated columns cross PCIe
         cwsl_host_free(g.audio);
-        g.audioElems = g.members.size() * afs;
+        g.audioElems = rows * afs;
         g.audio = static_cast<std::int16_t*>(cwsl_host_alloc(g.audioElems * sizeof(std::int16_t)));
         if (!g.audio) {
             g.audioElems = 0;
@@ -115,48 +209,66 @@ inline void Receiver::finishSlot(SlotGroup& g) {
         }
     }
     std::size_t wi = 0;
-    if (cwsl_rx_end_slot(rx, g.id, g.audio, &wi) != CWSL_OK || cwsl_rx_wait_output(rx) != CWSL_OK) {
-        screenPrinter->err(receiverLog() + std::string("slot failed: ") + cwsl_last_error());  // failed slot, carry on
-        g.startEpochTime = now;
-        return;
-    }
+    const bool ok = cwsl_rx_end_slot(rx, g.id, g.audio, &wi) == CWSL_OK && cwsl_rx_wait_output(rx) == CWSL_OK;
     const std::uint64_t startTime = g.startEpochTime;
     g.startEpochTime = now;  // stamp of the buffer that starts filling now (Instance.cpp:215)
-    if (0 == startTime) {
+    if (!ok) {
+        screenPrinter->err(receiverLog() + std::string("slot failed: ") + cwsl_last_error());  // failed slot, carry on
+    } else if (0 == startTime) {
         screenPrinter->debug(receiverLog() + "Discarding af buffer, start time is zero");  // Instance.cpp:224-227
-        return;
+    } else if (!g.idle) {
+        for (std::size_t m = 0; m < g.members.size(); ++m) {
+            Instance* inst = g.members[m];
+            std::vector<std::int16_t> audioBuf_i16(g.audio + m * afs, g.audio + (m + 1) * afs);
+            ItemToDecode toDecode(std::move(audioBuf_i16), inst->getMode(), startTime, inst->getFrequency(),
+                                  static_cast<int>(inst->getId()), inst->getCwd(), inst->getTRPeriod());
+            inst->getDecoderPool()->push(std::move(toDecode));  // Instance.cpp:244-245
+        }
+        ++nSlots;
     }
-    for (std::size_t m = 0; m < g.members.size(); ++m) {
-        Instance* inst = g.members[m];
-        std::vector<std::int16_t> audioBuf_i16(g.audio + m * afs, g.audio + (m + 1) * afs);
-        ItemToDecode toDecode(std::move(audioBuf_i16), inst->getMode(), startTime, inst->getFrequency(),
-                              static_cast<int>(inst->getId()), inst->getCwd(), inst->getTRPeriod());
-        inst->getDecoderPool()->push(std::move(toDecode));  // Instance.cpp:244-245
-    }
-    ++nSlots;
+    applyMembership(g);
 }
 
 inline void Receiver::readIQ() {
-    std::vector<float> block(2 * iq_len);
+    const std::size_t blockFloats = 2 * iq_len;
+    if (!staging) staging = static_cast<float*>(cwsl_host_alloc(kStagingBlocks * blockFloats * sizeof(float)));
+    if (!staging) {
+        screenPrinter->err(receiverLog() + std::string("IQ staging ring: ") + cwsl_last_error());
+        status = ReceiverStatus::STOPPED;
+        return;
+    }
+    std::uint64_t n = 0;  // blocks staged so far
     while (!terminateFlag) {
         // slot edges first, like the Instance does at the top of its loop (Instance.cpp:203-206)
         for (auto& g : groups) {
-            if (g.preds.front()->load()) {
+            if (!g.preds.empty() && g.preds.front()->load()) {
                 for (auto& p : g.preds) p->store(false);
                 finishSlot(g);
             }
         }
-        if (!source->readBlock(block.data())) {
+        const std::size_t slot = n % kStagingBlocks;
+        // refill a staging buffer only when the copy that last read it has completed (nothing else is waited for)
+        if (stagingFence[slot] && cwsl_rx_wait_fence(rx, stagingFence[slot]) != CWSL_OK)
+            screenPrinter->err(receiverLog() + std::string("staging fence: ") + cwsl_last_error());
+        float* block = staging + slot * blockFloats;
+        if (!source->readBlock(block)) {
             screenPrinter->debug(receiverLog() + "IQ producer ended");  // Receiver.hpp:235-237
             break;
         }
-        if (cwsl_rx_push_iq(rx, block.data(), 1) != CWSL_OK) {
-            screenPrinter->err(receiverLog() + std::string("push failed: ") + cwsl_last_error());
-            break;
+        ++n;
+        if (cwsl_rx_push_iq(rx, block, 1) != CWSL_OK) {
+            // like the reference's "ring buffer full" (Receiver.hpp:222-229): log, drop the block, carry on
+            screenPrinter->err(receiverLog() + std::string("push failed, block dropped: ") + cwsl_last_error());
+            ++nDroppedBlocks;
+            stagingFence[slot] = 0;
+            continue;
         }
-        // pageable source buffer is reused for the next block: wait for the copy
-        cwsl_rx_synchronize(rx);
+        if (cwsl_rx_push_fence(rx, &stagingFence[slot]) != CWSL_OK) {
+            stagingFence[slot] = 0;
+            cwsl_rx_synchronize(rx);  // no fence: fall back to a full wait before this buffer is reused
+        }
         ++nBlocks;
     }
+    cwsl_rx_synchronize(rx);
     status = ReceiverStatus::STOPPED;
 }

@@ -1,17 +1,25 @@
 // jt9 shared-memory hand-off: the segment layout and the per-mode parameter fill of
 // DecoderPool::decodeUsingShMem (source/DecoderPool.hpp:44-108 layout, :421-593 fill, :575-577 handshake).
 // `dec_data_t` is shared with WSJT-X's Fortran (lib/jt9com.f90) and must stay in sync with it.
-// What is NOT here: creating the segment under the key jt9 expects (the reference uses Qt's QSharedMemory,
-// i.e. a CreateFileMapping keyed by a Qt-mangled name on Windows) and spawning jt9 -- both out of scope.
-// fillDecData() works on any caller-provided block of sizeof(dec_data_t) bytes (e.g. the mapped segment, or
-// pinned memory the GPU result was copied into).
+// The reference creates the segment with Qt's QSharedMemory (a CreateFileMapping keyed by a Qt-mangled name on
+// Windows, source/DecoderPool.hpp:422-437); Jt9ShmSegment is its POSIX stand-in (shm_open + mmap under "/<key>"),
+// with the same life cycle: create -> fill -> decoder attaches by key -> handshake -> detach. Spawning jt9 itself
+// stays out of scope (Win32 CreateProcessA, binary not available). fillDecData() works on any block of
+// sizeof(dec_data_t) bytes (the mapped segment, or pinned memory the GPU result was copied into).
 #pragma once
 
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
 
-#include "DecoderPool.hpp"
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <string>
+
+#include "ItemToDecode.hpp"
 
 #define NSMAX 6827
 #define NTMAX (30 * 60)
@@ -117,3 +125,47 @@ inline bool fillDecData(dec_data_t* dec_data, const ItemToDecode& item, int high
     std::memcpy(&dec_data->d2[0], item.audio.data(), nel * sizeof(std::int16_t));
     return true;
 }
+
+// POSIX stand-in for QSharedMemory as the reference uses it (create(size) / attach by key / data() / detach).
+class Jt9ShmSegment {
+public:
+    Jt9ShmSegment() = default;
+    Jt9ShmSegment(const Jt9ShmSegment&) = delete;
+    Jt9ShmSegment& operator=(const Jt9ShmSegment&) = delete;
+    ~Jt9ShmSegment() { detach(); }
+    bool create(const std::string& key) { return open(key, true); }   // mem_jt9.create(sizeof(dec_data_t))
+    bool attach(const std::string& key) { return open(key, false); }  // what jt9 does with "-s <key>"
+    dec_data_t* data() const { return base; }
+    void detach() {
+        if (base) munmap(base, sizeof(dec_data_t));
+        if (fd >= 0) close(fd);
+        if (owner) shm_unlink(name.c_str());
+        base = nullptr;
+        fd = -1;
+        owner = false;
+    }
+
+private:
+    bool open(const std::string& key, bool creat) {
+        detach();
+        name = "/" + key;
+        fd = shm_open(name.c_str(), creat ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+        if (fd < 0) return false;
+        owner = creat;
+        if (creat && ftruncate(fd, sizeof(dec_data_t)) != 0) {
+            detach();
+            return false;
+        }
+        void* p = mmap(nullptr, sizeof(dec_data_t), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (p == MAP_FAILED) {
+            detach();
+            return false;
+        }
+        base = static_cast<dec_data_t*>(p);
+        return true;
+    }
+    std::string name;
+    int fd = -1;
+    dec_data_t* base = nullptr;
+    bool owner = false;
+};

@@ -7,11 +7,21 @@
 // for ALL decoders of that group in one batched GPU pass (cwsl_rx_end_slot), then builds one
 // ItemToDecode per decoder and hands it to DecoderPool::push -- the exact hand-off of
 // source/Instance.cpp:238-245. getIQBuffer() therefore has no consumers and is not provided.
+//
+// Ingest (source/Receiver.hpp:209-276): blocks are read from the IqSource straight into
+// a ring of PINNED staging buffers (cwsl_host_alloc) and pushed asynchronously; the reader only ever waits for the
+// host-to-device copy that last read the staging buffer it is about to refill (cwsl_rx_push_fence /
+// cwsl_rx_wait_fence), never for kernels or for the hand-off copies of finished slots.
+//
+// Decoders come and go while the receiver runs (the reference's main loop restarts FINISHED instances,
+// source/CWSL_DIGI.cpp:1217-1226): addInstance()/removeInstance() on a RUNNING receiver queue the request, and the
+// reader thread applies it at the slot group's next edge, where the GPU side changes its channel set as well.
 #pragma once
 
 #include <atomic>
 #include <chrono>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,6 +42,7 @@ public:
         if (status != ReceiverStatus::FINISHED) terminate();
         if (rx) cwsl_rx_destroy(rx);
         for (auto& g : groups) cwsl_host_free(g.audio);
+        cwsl_host_free(staging);
     }
 
     // opens the producer and creates the GPU front-end (source/Receiver.hpp:115-176 opens the shared
@@ -63,9 +74,13 @@ public:
     ReceiverStatus getStatus() { return status.load(); }
     const std::string& getName() const { return smname; }
 
-    // Called by Instance::init(): registers the decoder as a channel of the slot group that
-    // belongs to its SyncPredicate. Must happen before start().
+    // Called by Instance::init(): registers the decoder as a channel of the slot group that belongs to its
+    // SyncPredicate. On a RUNNING receiver the decoder joins at its group's next slot edge (the group, i.e. a decoder
+    // with the same period, must already exist: the set of periods is fixed once the receiver runs).
     bool addInstance(Instance* inst);
+    // Called by Instance::terminate(): the decoder leaves at its group's next slot edge (at once if the receiver is
+    // not running); its Instance object must stay alive until getStatus() of the instance reports FINISHED.
+    bool removeInstance(Instance* inst);
 
     // starts the reader thread (readIQ, source/Receiver.hpp:209-276)
     bool start() {
@@ -89,6 +104,8 @@ public:
 
     std::uint64_t blocksRead() const { return nBlocks.load(); }
     std::uint64_t slotsFinished() const { return nSlots.load(); }
+    std::uint64_t blocksDropped() const { return nDroppedBlocks.load(); }
+    static constexpr std::size_t kStagingBlocks = 16;  // pinned IQ staging ring (~170 ms at 192 kHz / 2048)
 
 private:
     // Decoders of this receiver that share a period = one GPU slot group. Every member keeps its own
@@ -102,10 +119,14 @@ private:
         std::uint64_t startEpochTime = 0;  // 0 = first, partial buffer -> discarded (Instance.cpp:224-227)
         std::int16_t* audio = nullptr;     // [members][af_size], pinned hand-off buffer (cwsl_host_alloc)
         std::size_t audioElems = 0;
+        std::vector<Instance*> joining, leaving;  // applied at the next slot edge (guarded by `mu`)
+        bool idle = false;  // every decoder of the group has terminated: the GPU group keeps one channel, nothing is handed on
     };
 
     void readIQ();
     void finishSlot(SlotGroup& g);
+    void applyMembership(SlotGroup& g);
+    bool attach(SlotGroup& g, Instance* inst);
     std::string receiverLog() const { return "Receiver " + smname + " "; }
 
     std::string smname;
@@ -121,5 +142,8 @@ private:
     std::thread iqThread;
     std::atomic<ReceiverStatus> status{ReceiverStatus::NOT_INITIALIZED};
     std::atomic_bool terminateFlag{false};
-    std::atomic<std::uint64_t> nBlocks{0}, nSlots{0};
+    std::atomic<std::uint64_t> nBlocks{0}, nSlots{0}, nDroppedBlocks{0};
+    std::mutex mu;            // membership requests from other threads
+    float* staging = nullptr; // [kStagingBlocks][2 * iq_len], pinned
+    std::uint64_t stagingFence[kStagingBlocks] = {};
 };

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <sstream>
 
+#include <future>
+
 #include "cwsl_host.hpp"
 
 static int g_fail = 0;
@@ -226,6 +228,67 @@ int main(int argc, char** argv) {
         EXPECT(fillDecData(dd.get(), f300, 3000, 3) && dd->params.nfa == 700 && dd->params.nfb == 1100 && dd->params.ndepth == 1 && dd->params.nmode == 240);
         ItemToDecode wspr(audio, "WSPR", 0, 14095600, 7, "cwd", 120.0f);
         EXPECT(!fillDecData(dd.get(), wspr, 3000, 3));           // WSPR always goes through a WAV file
+    }
+
+    // ---- transfermethod=shmem through the pool: segment life cycle + ipc[] handshake (source/DecoderPool.hpp:421-448,
+    //      :575-577, :689-709); WSPR / JS8 / FST4(W) still go through WAV files (:379-395) ----
+    {
+        auto printer = std::make_shared<ScreenPrinter>(LOG_LEVEL::ERR);
+        std::mutex m;
+        std::vector<std::string> keys, wavs;
+        std::vector<std::thread> decoders;
+        std::atomic<int> saw_data{0}, told_to_quit{0};
+        const std::string dir = "/tmp";
+        {
+            DecoderPool pool(
+                "shmem", dir, 2, 0, printer,
+                [&](const ItemToDecode&, const std::string& path) {
+                    std::lock_guard<std::mutex> lk(m);
+                    if (!path.empty()) wavs.push_back(path);
+                },
+                [&](const std::string& key, const ItemToDecode& item) {
+                    std::promise<bool> ready;
+                    auto fut = ready.get_future();
+                    std::lock_guard<std::mutex> lk(m);
+                    keys.push_back(key);
+                    decoders.emplace_back([&, key, item, p = std::move(ready)]() mutable {  // "jt9 -s <key>"
+                        Jt9ShmSegment seg;
+                        if (!seg.attach(key)) {
+                            p.set_value(false);
+                            return;
+                        }
+                        dec_data_t* d = seg.data();
+                        const bool same = std::memcmp(d->d2, item.audio.data(), item.audio.size() * 2) == 0;
+                        saw_data += same && d->ipc[1] == 1 && d->ipc[2] == -1 && d->params.nmode == (item.mode == "FT8" ? 8 : 5);
+                        p.set_value(true);
+                        volatile int* ipc = d->ipc;
+                        ipc[1] = 0;
+                        for (int i = 0; i < 5000 && ipc[2] != 1; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+                        told_to_quit += ipc[2] == 1 && ipc[1] == 999;
+                    });
+                    return fut.get();
+                });
+            pool.init();
+            std::vector<std::int16_t> a(240000), b(150000), w(1500000, 3);
+            for (size_t i = 0; i < a.size(); ++i) a[i] = static_cast<std::int16_t>(i * 7);
+            for (size_t i = 0; i < b.size(); ++i) b[i] = static_cast<std::int16_t>(i * 3 + 1);
+            pool.push(ItemToDecode(a, "FT8", 0, 14074000, 1, "cwd", 15.0f));
+            pool.push(ItemToDecode(b, "FT4", 0, 14080000, 2, "cwd", 7.5f));
+            pool.push(ItemToDecode(w, "WSPR", 0, 14095600, 3, "cwd", 120.0f));
+            pool.push(ItemToDecode(a, "FST4W-120", 0, 474200, 4, "cwd", 120.0f));
+            pool.drain();
+            EXPECT(pool.handled() == 4 && pool.handledViaShMem() == 2);
+            pool.terminate();
+        }
+        for (auto& t : decoders) t.join();
+        EXPECT(keys.size() == 2 && saw_data == 2 && told_to_quit == 2);
+        EXPECT(wavs.size() == 2);                                  // WSPR and FST4W-120 went through files
+        for (const auto& k : keys) {
+            Jt9ShmSegment gone;
+            EXPECT(!gone.attach(k));                               // detached and unlinked after the handshake
+            EXPECT(k.rfind("CWSL_DIGI_", 0) == 0);
+        }
+        for (const auto& p : wavs) std::remove(p.c_str());
     }
 
     if (g_fail) {

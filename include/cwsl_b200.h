@@ -44,12 +44,12 @@ extern "C" {
  *        channel of the slot group; each channel reads its NCO frequency off that grid (8-bin Kaiser-Bessel
  *        interpolation) and applies the reference's own float phase recurrence. Used for groups of >= 64 channels
  *        (CWSL_STFT_MIN_CHANNELS; the measured break-even with the FAST kernel); smaller groups run the FAST kernel.
- *        Contract: <= 1 int16 LSB, residual >= 90 dB below the channel's signal -- the same bars as FAST. The FFT's
- *        own error is NOT relative to the channel: it is the rounding noise of a float32 FFT, 1.7e-7 (-135 dB) of
- *        the rms of the whole band. The bars are kept by a dynamic-range guard: per segment of 1504 output samples,
- *        a channel whose mean power lies more than 42 dB (cwsl_rx_set_stft_guard) under the band's is recomputed by
- *        the FAST kernel on the device before the slot is normalised, so every sample handed on is either an FFT
- *        sample >= 93 dB above the FFT floor or a FAST sample.
+ *        Contract: the bars of FAST (<= 1 int16 LSB, residual >= 90 dB below the channel's signal wherever FAST
+ *        itself reaches them). The FFT's own error is NOT relative to the channel: it is the rounding noise of a
+ *        float32 FFT, 0.6e-7 ... 5.8e-7 (-144 ... -125 dB) of the rms of the whole band. The bars are kept by a
+ *        dynamic-range guard: per segment of 1504 output samples, a channel whose mean power lies more than 32 dB
+ *        (cwsl_rx_set_stft_guard) under the band's is recomputed by the FAST kernel on the device before the slot is
+ *        normalised, so every sample handed on is either an FFT sample >= 92 dB above the FFT floor or a FAST sample.
  * FAST and STFT results are functions of the slot's IQ alone: segment and anchor positions are fixed in
  * slot-relative coordinates, so equal IQ gives equal bytes however it was pushed (cwsl_rx_push_iq chunking,
  * cwsl_rx_process calls). For that the two modes demodulate whole segments only until the slot edge. */
@@ -112,7 +112,7 @@ void cwsl_rx_destroy(cwsl_rx_t* rx);
 int cwsl_rx_set_mode(cwsl_rx_t* rx, int mode);
 
 /* Threshold of the STFT mode's dynamic-range guard, in dB below the mean power of the band: channel segments whose
- * mean power is lower are recomputed in the direct form (see CWSL_MODE_STFT). Default 42 (CWSL_STFT_GUARD_DB);
+ * mean power is lower are recomputed in the direct form (see CWSL_MODE_STFT). Default 32 (CWSL_STFT_GUARD_DB);
  * 0 switches the guard off (diagnostics: the raw FFT channelizer). */
 int cwsl_rx_set_stft_guard(cwsl_rx_t* rx, double db_below_band_power);
 
@@ -151,6 +151,14 @@ size_t cwsl_rx_group_af_size(const cwsl_rx_t* rx, int group);
  * Asynchronous when `iq` is pinned memory. Slots that would lose un-demodulated samples to the
  * ring wrap are demodulated first. */
 int cwsl_rx_push_iq(cwsl_rx_t* rx, const float* iq, size_t n_blocks);
+
+/* Fences for callers that stage IQ in a ring of pinned buffers (source/Receiver.hpp:209-276 keeps such a ring on the
+ * host): cwsl_rx_push_fence marks the receiver's stream behind everything pushed so far and returns a token;
+ * cwsl_rx_wait_fence blocks until the work in front of that mark -- in particular the host-to-device copies that
+ * read the staging buffers -- has completed, without waiting for kernels or copies queued later. At most 64 fences
+ * are tracked; waiting for an older one waits for a younger one instead (never too short). */
+int cwsl_rx_push_fence(cwsl_rx_t* rx, uint64_t* token);
+int cwsl_rx_wait_fence(cwsl_rx_t* rx, uint64_t token);
 
 /* Same, source already in device memory on rx's device (device-to-device copy into the ring).
  * Stream semantics: the copy is queued on the receiver's stream (cwsl_rx_stream), which does not wait for any

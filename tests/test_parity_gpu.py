@@ -548,15 +548,23 @@ def test_stress_stft_channelizer(stress_run, ref):
         rx.bind_device_iq(x.data_ptr(), nblk)
         rx.end_slot(grp, None)
         st = rx.guard_stats(grp)
-        assert st["decided"] == 1024 * 120 and 0.5 * st["decided"] < st["redone"] < st["decided"]
+        assert st["decided"] == 1024 * 120 and 0.3 * st["decided"] < st["redone"] < st["decided"]
         rx.set_stft_guard(0.0)
         rx.bind_device_iq(x.data_ptr(), nblk)
         rx.end_slot(grp, None)
         assert rx.guard_stats(grp)["decided"] == 0
-        raw_off = rx.read_float_audio(grp, 1)
-    r_off = resid_db(raw_off[:wi], fraw[1][:wi])
-    print(f"guard off, noise-only channel 1 vs fast: {r_off:.1f} dB")
-    assert -100.0 < r_off < -80.0          # the float32-FFT floor the guard exists for
+        quiet = [10, 522, 979]               # noise only: the sixteen tones sit in channels 64 k - 29 ... 64 k + 3
+        raw_off = {c: rx.read_float_audio(grp, c) for c in quiet}
+    with cw.Receiver(0, fs, iq_len, mode=cw.MODE_EXACT) as rx:
+        grp = rx.add_group(15.0)
+        for c in quiet:
+            rx.add_channel(grp, int(freqs[c]), 0.9)
+        rx.bind_device_iq(x.data_ptr(), nblk)
+        rx.end_slot(grp, None)
+        exact = {c: rx.read_float_audio(grp, i) for i, c in enumerate(quiet)}
+    r_off = max(resid_db(raw_off[c][:wi], exact[c][:wi]) for c in quiet)
+    print(f"guard off, noise-only channels vs the bit-exact mode: worst {r_off:.1f} dB")
+    assert -100.0 < r_off < -80.0          # the float32-FFT floor the guard exists for (measured -88.8 dB)
 
 
 def test_stft_guard_high_dynamic_range(gpu, ref):
