@@ -313,6 +313,8 @@ def run_b200(a):
         s_.wait_event(e0)
     for _ in range(a.steps):
         step_resident()
+    for rx in rxs:                              # the last slots' quantise / max reset (post streams) belong to the region
+        rx.join_output()
     for s_ in rx_streams:                       # join
         ev = torch.cuda.Event()
         ev.record(s_)
@@ -433,6 +435,8 @@ def run_b200(a):
             f0.record(stream)
             step_resident()
             step_resident()
+            for rx in rxs:
+                rx.join_output()
             f1.record(stream)
             barrier()
             tm = torch.tensor([f0.elapsed_time(f1) / 2], device="cuda", dtype=torch.float64)

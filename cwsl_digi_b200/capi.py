@@ -20,7 +20,7 @@ SYMBOLS = [
     "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_wait_output", "cwsl_rx_stream", "cwsl_rx_set_stream", "cwsl_rx_enable_timing",
     "cwsl_rx_kernel_times", "cwsl_measure_fp32_peak", "cwsl_host_alloc", "cwsl_host_free",
     "cwsl_rx_set_stft_guard", "cwsl_rx_remove_channel", "cwsl_rx_kernel_times_ex", "cwsl_rx_guard_stats",
-    "cwsl_rx_push_fence", "cwsl_rx_wait_fence",
+    "cwsl_rx_push_fence", "cwsl_rx_wait_fence", "cwsl_rx_join_output",
 ]
 
 
@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
     L.cwsl_rx_remove_channel.argtypes = [vp, C.c_int, C.c_int]
     L.cwsl_rx_kernel_times_ex.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.cwsl_rx_guard_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.cwsl_rx_join_output.argtypes = [vp]
     L.cwsl_rx_push_fence.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.cwsl_rx_wait_fence.argtypes = [vp, C.c_uint64]
     L.cwsl_host_alloc.restype = vp
@@ -312,6 +313,10 @@ class Receiver:
 
     def synchronize(self) -> None:
         _check(self._L.cwsl_rx_synchronize(self._h))
+
+    def join_output(self) -> None:
+        """Device-side: later work on the receiver's stream waits for the last slot's post work (no host blocking)."""
+        _check(self._L.cwsl_rx_join_output(self._h))
 
     def wait_output(self) -> None:
         _check(self._L.cwsl_rx_wait_output(self._h))

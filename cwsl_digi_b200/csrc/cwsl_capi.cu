@@ -1303,6 +1303,13 @@ int cwsl_rx_wait_output(cwsl_rx_t* rx) {
     return CWSL_OK;
 }
 
+int cwsl_rx_join_output(cwsl_rx_t* rx) {
+    if (!rx) return fail(CWSL_ERR_INVALID, "null receiver");
+    DeviceGuard dg(rx->device);
+    if (rx->d2h_pending) CK(cudaStreamWaitEvent(rx->stream, rx->ev_d2h_done, 0));
+    return CWSL_OK;
+}
+
 void* cwsl_rx_stream(cwsl_rx_t* rx) { return rx ? (void*)rx->stream : nullptr; }
 
 int cwsl_rx_kernel_times_ex(cwsl_rx_t* rx, float ms[5], int launches[2]) {

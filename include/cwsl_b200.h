@@ -223,6 +223,11 @@ int cwsl_rx_synchronize(cwsl_rx_t* rx);
  * hand-off buffer is needed. */
 int cwsl_rx_wait_output(cwsl_rx_t* rx);
 
+/* Device-side join, no host blocking: whatever is queued on the receiver's stream after this call starts only when
+ * the post work of the last cwsl_rx_end_slot (normalise/quantise, max reset, host copy -- they run on a private
+ * post stream) has finished. For callers that bracket several receivers with events on one shared stream. */
+int cwsl_rx_join_output(cwsl_rx_t* rx);
+
 /* The CUDA stream (cudaStream_t) all work of this receiver is queued on, for event timing. */
 void* cwsl_rx_stream(cwsl_rx_t* rx);
 
