@@ -36,8 +36,16 @@ def main(rep, out_csv, traffic_json=None, label=""):
             v, u = d[key]
             return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
         rd, wr = tobytes('dram__bytes_read.sum'), tobytes('dram__bytes_write.sum')
+        def num(key):
+            return float(d[key][0]) if key in d else None
         json.dump({"kernel": d.get("Kernel Name", ("", ""))[0] + " " + label, "dram_bytes_per_launch": rd + wr,
                    "dram_bytes_read": rd, "dram_bytes_write": wr,
+                   "lsu_shared_wavefronts_per_launch": (num('l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum') or 0)
+                   + (num('l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum') or 0),
+                   "fma_pipe_pct": num('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed'),
+                   "issue_active_pct": num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                   "shared_wavefront_pct": num('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed'),
+                   "duration_us": num('gpu__time_duration.sum'),
                    "source": f"ncu --set full --clock-control none ({rep})"}, open(traffic_json, "w"), indent=1)
 
 

@@ -2,6 +2,7 @@
 buffer allocated (a) wherever the process happens to run, (b) on the GPU's own NUMA node, (c) on another node.
 Run under torchrun: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/numa_probe.py"""
 import glob
+import json
 import os
 import subprocess
 import time
@@ -46,6 +47,8 @@ def main():
     n = 1 << 30
     dev = torch.empty(n, dtype=torch.uint8, device="cuda")
 
+    results = {}
+
     def run(tag, cpus):
         if cpus:
             os.sched_setaffinity(0, cpus)
@@ -66,8 +69,26 @@ def main():
             res[name] = 10 * n / dt / 1e9
             if world > 1:
                 dist.barrier()
-        print(f"rank {rank} {tag}: d2h {res['d2h']:.1f} GB/s  h2d {res['h2d']:.1f} GB/s", flush=True)
-        del host
+        # both directions at once (the end-to-end leg pushes the next receiver's IQ while a slot is copied back)
+        host2 = torch.empty(n // 16, dtype=torch.uint8).pin_memory()
+        dev2 = torch.empty(n // 16, dtype=torch.uint8, device="cuda")
+        s2 = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            host.copy_(dev, non_blocking=True)
+            with torch.cuda.stream(s2):
+                dev2.copy_(host2, non_blocking=True)
+        torch.cuda.synchronize()
+        res["d2h_duplex"] = 10 * n / (time.perf_counter() - t0) / 1e9
+        if world > 1:
+            dist.barrier()
+        print(f"rank {rank} {tag}: d2h {res['d2h']:.1f} GB/s  h2d {res['h2d']:.1f} GB/s  d2h with 1/16 h2d beside it "
+              f"{res['d2h_duplex']:.1f} GB/s", flush=True)
+        results[tag] = res
+        del host, host2, dev2
 
     run("default placement", None)
     if node >= 0 and len(nodes) > 1:
@@ -86,8 +107,28 @@ def main():
             for _ in range(10):
                 host.copy_(dev, non_blocking=True)
             torch.cuda.synchronize()
-            print(f"rank {rank} solo d2h {10 * n / (time.perf_counter() - t0) / 1e9:.1f} GB/s", flush=True)
+            results["solo"] = {"d2h": 10 * n / (time.perf_counter() - t0) / 1e9}
+            print(f"rank {rank} solo d2h {results['solo']['d2h']:.1f} GB/s", flush=True)
             del host
+    mine = dict(rank=rank, gpu=local, bus=busid, numa_node=node, results=results)
+    if world > 1:
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+    else:
+        allr = [mine]
+    if rank == 0:
+        conc = [r["results"]["default placement"] for r in allr]
+        summary = dict(
+            n_ranks=world, host_cpus=os.cpu_count(), numa_nodes=nodes, bytes_per_copy=n, copies=10,
+            what="plain pinned cudaMemcpyAsync ceilings, all ranks copying at the same time (1 GiB buffers, 10 copies, wall "
+                 "clock around a device synchronize) and one rank at a time (solo)",
+            concurrent_d2h_gbs_per_rank=[c["d2h"] for c in conc], concurrent_h2d_gbs_per_rank=[c["h2d"] for c in conc],
+            concurrent_d2h_duplex_gbs_per_rank=[c["d2h_duplex"] for c in conc],
+            concurrent_d2h_gbs_total=sum(c["d2h"] for c in conc), concurrent_h2d_gbs_total=sum(c["h2d"] for c in conc),
+            solo_d2h_gbs_per_rank=[r["results"]["solo"]["d2h"] for r in allr], ranks=allr)
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(summary, open(f"gpurun_out/r2_numa_probe_n{world}.json", "w"), indent=1)
+        print(json.dumps({k: v for k, v in summary.items() if k != "ranks"}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
