@@ -6,7 +6,7 @@ is only a thin ctypes binding used by the tests and bench.py; it contains no com
 CPU fallback: if the library is missing it raises.
 """
 from .capi import (CwslError, Receiver, HostBuffer, MODE_EXACT, MODE_FAST, MODE_STFT, af_size, accepted_blocks,  # noqa: F401
-                   build_tables, stft_tables, stft_channel, ssbd_params, device_count, measure_fp32_peak, lib, lib_path, build_library)
+                   build_tables, stft_tables, stft_channel, stft_items, ssbd_params, device_count, measure_fp32_peak, lib, lib_path, build_library)
 
-__all__ = ["CwslError", "Receiver", "HostBuffer", "MODE_EXACT", "MODE_FAST", "MODE_STFT", "af_size", "accepted_blocks", "build_tables", "stft_tables", "stft_channel",
+__all__ = ["CwslError", "Receiver", "HostBuffer", "MODE_EXACT", "MODE_FAST", "MODE_STFT", "af_size", "accepted_blocks", "build_tables", "stft_tables", "stft_channel", "stft_items",
            "ssbd_params", "device_count", "measure_fp32_peak", "lib", "lib_path", "build_library"]

@@ -20,7 +20,7 @@ SYMBOLS = [
     "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_wait_output", "cwsl_rx_stream", "cwsl_rx_set_stream", "cwsl_rx_enable_timing",
     "cwsl_rx_kernel_times", "cwsl_measure_fp32_peak", "cwsl_host_alloc", "cwsl_host_free",
     "cwsl_rx_set_stft_guard", "cwsl_rx_remove_channel", "cwsl_rx_kernel_times_ex", "cwsl_rx_guard_stats",
-    "cwsl_rx_push_fence", "cwsl_rx_wait_fence", "cwsl_rx_join_output",
+    "cwsl_rx_push_fence", "cwsl_rx_wait_fence", "cwsl_rx_join_output", "cwsl_stft_items",
 ]
 
 
@@ -101,6 +101,7 @@ def lib() -> C.CDLL:
     L.cwsl_rx_kernel_times_ex.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.cwsl_rx_guard_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.cwsl_rx_join_output.argtypes = [vp]
+    L.cwsl_stft_items.argtypes = [C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32)]
     L.cwsl_rx_push_fence.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.cwsl_rx_wait_fence.argtypes = [vp, C.c_uint64]
     L.cwsl_host_alloc.restype = vp
@@ -164,6 +165,20 @@ def stft_channel(fs: int, demod_freq: int, is_usb: bool = True) -> dict:
     rot = np.zeros(2, np.float32)
     _check(lib().cwsl_stft_channel(fs, demod_freq, int(is_usb), C.byref(q0), wgt.ctypes.data, rot.ctypes.data))
     return dict(q0=q0.value, wgt=wgt, rot=complex(rot[0], rot[1]))
+
+
+def stft_items(fs: int, demod_freqs, is_usb=None) -> dict:
+    """Work items of the channelizer kernel for a channel set: first_bin [n_items], channels [n_items, 4] (-1: empty
+    slot), weights [n_items, 4, 9]; member j of an item reads bins first_bin + (0, 0, 1, 2)[j] ... + 8."""
+    f = np.ascontiguousarray(demod_freqs, np.int32)
+    u = np.ascontiguousarray(np.ones(f.size, np.int32) if is_usb is None else np.asarray(is_usb, np.int32))
+    first = np.zeros(f.size, np.int32)
+    chans = np.full((f.size, 4), -1, np.int32)
+    w = np.zeros((f.size, 4, 9), np.float32)
+    n = C.c_uint32()
+    _check(lib().cwsl_stft_items(fs, f.ctypes.data, u.ctypes.data, f.size, first.ctypes.data, chans.ctypes.data,
+                                 w.ctypes.data, C.byref(n)))
+    return dict(first_bin=first[:n.value], channels=chans[:n.value], weights=w[:n.value], shift=np.array([0, 0, 1, 2]))
 
 
 def measure_fp32_peak(device: int = 0) -> dict:

@@ -116,7 +116,8 @@ struct Group {
     float* d_maxval = nullptr;
     float* d_audio = nullptr;
     int16_t* d_out = nullptr;
-    cwsl::ChanConst* d_chan = nullptr;  // STFT channelizer constants
+    cwsl::ChanItem* d_chan = nullptr;   // STFT channelizer work items (<= 4 neighbouring channels each)
+    uint32_t n_chan_items = 0;
     // STFT mode only, allocated at its first use (ensure_stft): anchors of the exact phase recurrence and the
     // dynamic-range guard's per-launch scratch
     const float2* d_anchors = nullptr;  // shared, see g_anchor_cache
@@ -369,20 +370,34 @@ int commit_group_impl(cwsl_rx* rx, Group& g) {
     CK(cudaMemcpyAsync(g.d_scale, scale.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
     CK(cudaMemsetAsync(g.d_maxbits, 0, C * sizeof(unsigned), rx->stream));
     CK(cudaMemsetAsync(g.d_counters, 0, 4 * sizeof(unsigned long long), rx->stream));
-    std::vector<cwsl::ChanConst> cconst(C);
-    for (uint32_t c = 0; c < C; ++c) {  // STFT channelizer constants (CWSL_MODE_STFT)
-        const cwsl::ChanChannel cc = cwsl::chan_channel(rx->geo, g.ch[c].nco, cwsl::kChanKernelWidth, cwsl::kChanTaps);
-        cconst[c].q0 = cc.q0;
-        cconst[c].sign = g.ch[c].nco.sign;
-        cconst[c].rot[0] = cc.rot.real();
-        cconst[c].rot[1] = cc.rot.imag();
-        for (int i = 0; i < cwsl::kChanTaps; ++i) cconst[c].wgt[i] = cc.wgt[i];
-        cconst[c].pinc[0] = g.ch[c].nco.phase_inc.real();
-        cconst[c].pinc[1] = g.ch[c].nco.phase_inc.imag();
-        cconst[c].pad[0] = cconst[c].pad[1] = 0.0f;
+    // STFT channelizer work items (CWSL_MODE_STFT): channels in ascending grid position, <= 4 neighbours per item
+    std::vector<cwsl::NcoTables> ncos(C);
+    for (uint32_t c = 0; c < C; ++c) ncos[c] = g.ch[c].nco;
+    const std::vector<cwsl::ChanItemHost> hitems =
+        cwsl::chan_item_order(cwsl::chan_items(rx->geo, ncos, cwsl::kChanKernelWidth), (int)cwsl::chan_grid(rx->geo), cwsl::kChanMaxItems);
+    std::vector<cwsl::ChanItem> items(hitems.size());
+    const int grid_bins = (int)cwsl::chan_grid(rx->geo);
+    for (size_t i = 0; i < hitems.size(); ++i) {
+        const cwsl::ChanItemHost& h = hitems[i];
+        cwsl::ChanItem& it = items[i];
+        std::memset(&it, 0, sizeof(it));
+        it.bin_off = (uint32_t)(((h.e % grid_bins) + grid_bins) % grid_bins) * 8u;
+        it.n_members = (uint32_t)h.n;
+        for (int j = 0; j < cwsl::kChanItemMembers; ++j) {
+            it.ch[j] = h.ch[j] < 0 ? 0xffffffffu : (uint32_t)h.ch[j];
+            if (h.ch[j] < 0) continue;
+            const ChannelHost& ch = g.ch[h.ch[j]];
+            it.sign[j] = ch.nco.sign;
+            it.pinc[j][0] = ch.nco.phase_inc.real();
+            it.pinc[j][1] = ch.nco.phase_inc.imag();
+            it.rot[j][0] = h.rot[j].real();
+            it.rot[j][1] = h.rot[j].imag();
+            for (int q = 0; q < cwsl::kChanItemTaps; ++q) it.w[j][q] = h.w[j][q];
+        }
     }
-    CK(cudaMalloc(&g.d_chan, C * sizeof(cwsl::ChanConst)));
-    CK(cudaMemcpyAsync(g.d_chan, cconst.data(), C * sizeof(cwsl::ChanConst), cudaMemcpyHostToDevice, rx->stream));
+    g.n_chan_items = (uint32_t)items.size();
+    CK(cudaMalloc(&g.d_chan, items.size() * sizeof(cwsl::ChanItem)));
+    CK(cudaMemcpyAsync(g.d_chan, items.data(), items.size() * sizeof(cwsl::ChanItem), cudaMemcpyHostToDevice, rx->stream));
     CK(cudaStreamSynchronize(rx->stream));  // host vectors go out of scope
 
     // phase tables: one per distinct (Fs, demodFreq, sideband, length), shared process-wide. New tables are built
@@ -605,7 +620,8 @@ int process_group(cwsl_rx* rx, Group& g, bool final) {
         else
             CK(cwsl::launch_demod_exact(p, rx->stream));
     } else if (stft) {
-        // big channel groups: one FFT per hop shared by all channels, <= kChanMaxChannels channels per launch;
+        // big channel groups: one FFT per hop shared by all channels, <= kChanMaxItems work items (of up to 4
+        // neighbouring channels) per launch;
         // channel segments too close to the FFT's noise floor are redone by the direct-form kernel (cwsl_guard.cu)
         const bool guard = rx->guard_db > 0;
         cwsl::GuardLaunch gl;
@@ -627,25 +643,22 @@ int process_group(cwsl_rx* rx, Group& g, bool final) {
             ev.e_main = get_event(rx);
             CK(cudaEventRecord(ev.e_pre, rx->stream));
         }
-        for (uint32_t c0 = 0; c0 < p.n_channels; c0 += cwsl::kChanMaxChannels) {
-            cwsl::DemodLaunch q = p;
-            q.n_channels = std::min<uint32_t>(cwsl::kChanMaxChannels, p.n_channels - c0);
-            q.audio = p.audio + (size_t)c0 * p.af_stride;
-            q.maxbits = p.maxbits + c0;
+        for (uint32_t i0 = 0; i0 < g.n_chan_items; i0 += cwsl::kChanMaxItems) {
             cwsl::ChanLaunch c;
             c.window = rx->chan_tables.window;
             c.twiddle = rx->chan_tables.twiddle;
-            c.consts = g.d_chan + c0;
-            c.anchors = g.d_anchors + c0;
+            c.items = g.d_chan + i0;
+            c.n_items = std::min<uint32_t>(cwsl::kChanMaxItems, g.n_chan_items - i0);
+            c.anchors = g.d_anchors;
             c.anchor_stride = p.n_channels;
             if (guard) {
                 c.seg_blocks = seg;
-                c.seg_max = g.d_seg_max + c0;
-                c.seg_energy = g.d_seg_energy + c0;
+                c.seg_max = g.d_seg_max;
+                c.seg_energy = g.d_seg_energy;
                 c.seg_scale = g.d_seg_scale;
                 c.stat_stride = p.n_channels;
             }
-            CK(cwsl::launch_demod_chan(q, c, rx->stream));
+            CK(cwsl::launch_demod_chan(p, c, rx->stream));
         }
         if (rx->timing) CK(cudaEventRecord(ev.e_main, rx->stream));
         if (guard) {
@@ -798,6 +811,33 @@ int cwsl_stft_channel(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, i
         rot[0] = c.rot.real();
         rot[1] = c.rot.imag();
     }
+    return CWSL_OK;
+}
+
+int cwsl_stft_items(uint32_t sample_rate, const int32_t* demod_freq_hz, const int* is_usb, uint32_t n, int32_t* first_bin,
+                    int32_t* channels, float* weights, uint32_t* n_items) {
+    cwsl::SsbdGeometry g;
+    if (!cwsl::ssbd_geometry(sample_rate, &g)) return fail(CWSL_ERR_INVALID, "Fs/B must be an even integer >= 4");
+    if (g.block_size != 16 && g.block_size != 8 && g.block_size != 4)
+        return fail(CWSL_ERR_INVALID, "the STFT channelizer is built for 192, 96 and 48 kHz receivers");
+    if (!demod_freq_hz || !n_items) return fail(CWSL_ERR_INVALID, "null argument");
+    std::vector<cwsl::NcoTables> nco(n);
+    for (uint32_t c = 0; c < n; ++c)
+        if (!cwsl::nco_tables(g, demod_freq_hz[c], is_usb ? is_usb[c] != 0 : true, &nco[c]))
+            return fail(CWSL_ERR_INVALID, "Signal outside of band");
+    // in the kernel's own thread order (launches of kChanMaxItems items, one item per interpolation thread)
+    const std::vector<cwsl::ChanItemHost> items =
+        cwsl::chan_item_order(cwsl::chan_items(g, nco, cwsl::kChanKernelWidth), (int)cwsl::chan_grid(g), cwsl::kChanMaxItems);
+    for (size_t i = 0; i < items.size(); ++i) {
+        if (first_bin) first_bin[i] = items[i].e;
+        for (int j = 0; j < cwsl::kItemMembers; ++j) {
+            if (channels) channels[i * cwsl::kItemMembers + j] = items[i].ch[j];
+            if (weights)
+                for (int q = 0; q < cwsl::kItemTaps; ++q)
+                    weights[(i * cwsl::kItemMembers + j) * cwsl::kItemTaps + q] = items[i].w[j][q];
+        }
+    }
+    *n_items = (uint32_t)items.size();
     return CWSL_OK;
 }
 

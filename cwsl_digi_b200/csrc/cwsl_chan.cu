@@ -24,10 +24,14 @@
 //              history before the slot start, source/Instance.cpp:251), N-point FFT as (N/32) x 32 -- two
 //              register-resident radix-2 DIF passes with one transpose through the hop's own spectrum buffer --
 //              window, inter-pass twiddles and the centring rotation i^q from small L1-resident tables;
-//   warps 8-15 (consumers) own up to 4 channels per thread for the whole launch (stencil offset, 8 weights, rot*P and
-//              phase_inc in registers): per hop 4 x LDS.128 + 8 x FFMA2, Weaver select (source/SSBD.hpp:132-135),
-//              R <- R * phase_inc with R re-read from the exact phase table every 128 hops, one 32-byte store per
-//              channel and 8 hops, max|x| in a register until the end (one atomicMax per channel and CTA);
+//   warps 8-15 (consumers) own one work ITEM per thread for the whole launch: up to 4 channels that are neighbours on
+//              the FFT grid (cwsl_tables.hpp chan_items) and therefore read ONE 12-bin window -- 6 x LDS.128 per hop
+//              serve four channels (each channel alone would need 4: shared-memory wavefronts were this kernel's
+//              limit). Weights (4 x 9, zero outside the kernel's support), rot*P and phase_inc live in registers;
+//              per hop and channel 9 x FFMA2, Weaver select (source/SSBD.hpp:132-135), R <- R * phase_inc with R
+//              re-read from the exact phase table every 128 hops, one 32-byte store per channel and 8 hops, max|x| in
+//              a register until the end (one atomicMax per channel and CTA);
+//   registers move from the FFT warps to the interpolation warps at the role split (setmaxnreg);
 //   spectra are handed over through a ring of three shared-memory buffers with named barriers (bar.arrive /
 //   bar.sync), so the FFT warps run up to two batches ahead of the interpolation warps.
 #include "cwsl_kernels.hpp"
@@ -58,8 +62,15 @@ struct ChanGeo {
     // float2 per hop buffer: A rows of 34 during the transpose, N (+8 wrapped) bins after; the 8-row geometry gets 8
     // more so that the two hops of a half-warp sit 16 banks apart
     static constexpr int kHop = kA * kRow + (kA == 8 ? 8 : 0);
-    static_assert(kN + 8 <= kHop, "wrapped stencil bins must fit");
+    static constexpr int kWrap = kChanItemBins - 2;  // bins 0..9 again behind bin N-1: a 12-bin window never wraps
+    static_assert(kN + kWrap <= kHop, "wrapped stencil bins must fit");
 };
+
+// d * (wr + i wi) as two packed instructions: FMUL2 with the broadcast real part, then FFMA2 of the rotated operand
+// (-d.y, d.x) -- ptxas folds the swap/negate into the FFMA2 operand modifiers -- with the broadcast imaginary part.
+__device__ __forceinline__ float2 cmul_pk(float2 d, float wr, float wi) {
+    return ffma2(make_float2(-d.y, d.x), bc(wi), fmul2(d, bc(wr)));
+}
 
 // W32^k = exp(-2 pi i k / 32), k = 0..15
 __device__ __forceinline__ float2 mul_w32(float2 d, int k) {
@@ -69,21 +80,21 @@ __device__ __forceinline__ float2 mul_w32(float2 d, int k) {
     constexpr float c4 = 0.70710678118654752440f;
     switch (k) {
         case 0: return d;
-        case 1: return make_float2(d.x * c1 + d.y * s1, d.y * c1 - d.x * s1);
-        case 2: return make_float2(d.x * c2 + d.y * s2, d.y * c2 - d.x * s2);
-        case 3: return make_float2(d.x * c3 + d.y * s3, d.y * c3 - d.x * s3);
-        case 4: return make_float2((d.x + d.y) * c4, (d.y - d.x) * c4);
-        case 5: return make_float2(d.x * s3 + d.y * c3, d.y * s3 - d.x * c3);
-        case 6: return make_float2(d.x * s2 + d.y * c2, d.y * s2 - d.x * c2);
-        case 7: return make_float2(d.x * s1 + d.y * c1, d.y * s1 - d.x * c1);
+        case 1: return cmul_pk(d, c1, -s1);
+        case 2: return cmul_pk(d, c2, -s2);
+        case 3: return cmul_pk(d, c3, -s3);
+        case 4: return cmul_pk(d, c4, -c4);
+        case 5: return cmul_pk(d, s3, -c3);
+        case 6: return cmul_pk(d, s2, -c2);
+        case 7: return cmul_pk(d, s1, -c1);
         case 8: return make_float2(d.y, -d.x);
-        case 9: return make_float2(d.y * c1 - d.x * s1, -(d.x * c1 + d.y * s1));
-        case 10: return make_float2(d.y * c2 - d.x * s2, -(d.x * c2 + d.y * s2));
-        case 11: return make_float2(d.y * c3 - d.x * s3, -(d.x * c3 + d.y * s3));
-        case 12: return make_float2((d.y - d.x) * c4, -(d.x + d.y) * c4);
-        case 13: return make_float2(d.y * s3 - d.x * c3, -(d.x * s3 + d.y * c3));
-        case 14: return make_float2(d.y * s2 - d.x * c2, -(d.x * s2 + d.y * c2));
-        default: return make_float2(d.y * s1 - d.x * c1, -(d.x * s1 + d.y * c1));
+        case 9: return cmul_pk(d, -s1, -c1);
+        case 10: return cmul_pk(d, -s2, -c2);
+        case 11: return cmul_pk(d, -s3, -c3);
+        case 12: return cmul_pk(d, -c4, -c4);
+        case 13: return cmul_pk(d, -c3, -s3);
+        case 14: return cmul_pk(d, -c2, -s2);
+        default: return cmul_pk(d, -c1, -s1);
     }
 }
 
@@ -145,6 +156,7 @@ __device__ __forceinline__ void bar_sync(int id, int count) {
 __device__ __forceinline__ void bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+
 __device__ __forceinline__ void stg256(float* dst, const float (&o)[8]) {  // one 32-byte sector per lane (STG.256)
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
                  "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
@@ -153,23 +165,44 @@ __device__ __forceinline__ void stg256(float* dst, const float (&o)[8]) {  // on
 
 constexpr int kFftWarps = 8;
 constexpr int kFftThreads = 32 * kFftWarps;
-constexpr int kIntThreads = 256;  // interpolation threads per CTA, each owns up to KC channels for the whole launch
+constexpr int kIntThreads = 256;  // interpolation threads per CTA, each owns one work item (<= 4 channels) for the whole launch
 constexpr int kThreads = kFftThreads + kIntThreads;
+// Registers: the kernel starts with kLaunchRegs per thread; at the role split the FFT warps give registers back and the
+// interpolation warps (4 x 9 weights + a 12-bin window + 32 outputs in flight per thread) take them (setmaxnreg).
+// 512 x 120 leaves 4 K registers per SM for a CTA of the (HBM-bound) quantise kernel of the previous receiver, which
+// then runs underneath this (shared-memory-bound) kernel instead of after it.
+constexpr int kLaunchRegs = 120, kFftRegs = 96, kIntRegs = 144;
+static_assert(kFftThreads * kFftRegs + kIntThreads * kIntRegs <= kThreads * kLaunchRegs, "register budget");
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 // IQ staging ring in shared memory: stages of one batch worth of new samples (HB blocks = 1 KB at every rate),
-// brought in by the TMA bulk-copy engine kIqPrefetch batches ahead of the FFT warps. 16 stages: a batch reads the
+// brought in by the TMA bulk-copy engine iq_prefetch() batches ahead of the FFT warps. 16 stages at 192 kHz: a batch reads the
 // newest stage and the <= 4 before it (the 31 blocks of filter history), 3 are in flight, and the FFT warps are never
 // more than kBufs batches apart (they meet the interpolation warps at the spectrum ring), so a stage is overwritten
 // long after its last reader -- no "empty" barrier is needed.
-constexpr int kIqStages = 16;
-constexpr int kIqPrefetch = 3;
+template <int BS>
+__host__ __device__ constexpr int iq_stages() { return BS == 4 ? 8 : 16; }    // (48 kHz: batches of 32 hops; the smaller ring makes room
+template <int BS>
+__host__ __device__ constexpr int iq_prefetch() { return BS == 4 ? 1 : 3; }  //  for the 210 KB of spectrum buffers of that geometry)
 template <int BS>
 __host__ __device__ constexpr size_t spec_bytes() {  // 3 buffers x (8 FFT warps x HW hops) x hop buffer: 204 KB at every rate
     return (size_t)kBufs * ChanGeo<BS>::kHB * ChanGeo<BS>::kHop * 8;
 }
 template <int BS>
 __host__ __device__ constexpr size_t iq_stage_bytes() { return (size_t)ChanGeo<BS>::kHB * BS * 8; }  // 1 KB
+// Per-lane constants of the FFT warps, one padded record per lane (conflict-free LDS.128): the inter-pass twiddle
+// W_N^(lane q1) i^q1 split as T1[q1 >> 2] * T2[q1 & 3] (A/4 + 4 complex values instead of A, so they are re-read from
+// shared memory per hop instead of from L1 per use), then the lane's A/2 window taps.
 template <int BS>
-__host__ __device__ constexpr size_t chan_smem_bytes() { return spec_bytes<BS>() + kIqStages * iq_stage_bytes<BS>() + kIqStages * 8; }
+__host__ __device__ constexpr int lane_rec_floats() { return ChanGeo<BS>::kA + 8; }
+template <int BS>
+__host__ __device__ constexpr int lane_rec_stride() { return ChanGeo<BS>::kA + 12; }  // floats; 44 / 28 / 20: odd multiples of 4
+template <int BS>
+__host__ __device__ constexpr size_t chan_smem_bytes() {
+    return spec_bytes<BS>() + iq_stages<BS>() * iq_stage_bytes<BS>() + iq_stages<BS>() * 8 + 32 * lane_rec_stride<BS>() * 4;
+}
 
 // Complex multiply with a FIXED contraction pattern: the per-hop NCO step R <- R * phase_inc between anchors must
 // give the same bits wherever it is evaluated (in the hop loop, or replayed from the anchor at the start of a CTA's
@@ -184,14 +217,13 @@ __device__ __forceinline__ float2 cmul_fix(float2 a, float2 b) {
 // barriers (bar.arrive / bar.sync), no __syncthreads in the loop. The IQ samples reach the FFT warps through a
 // shared-memory ring filled by cp.async.bulk (TMA) with mbarrier completion: each sample crosses L2 -> SM once per
 // CTA run instead of once per hop that covers it (32x).
-// 104 registers x 512 threads leave room on every SM for CTAs of the (HBM-bound) quantise kernel of the previous
-// receiver, which then runs underneath this (shared-memory-bound) kernel instead of after it.
-template <int BS, int KC>
-__global__ void __maxnreg__(104)
+template <int BS>
+__global__ void __maxnreg__(kLaunchRegs)
     demod_chan_kernel(DemodLaunch p, ChanLaunch c, uint32_t n_batches, uint32_t batches_per_cta) {
     using G = ChanGeo<BS>;
     constexpr int A = G::kA, HW = G::kHW, HB = G::kHB, HOP = G::kHop, N = G::kN;
     constexpr int P0 = (31 + HB - 1) / HB;   // stages of filter history in front of a batch's own stage: 4 / 2 / 1
+    constexpr int kIqStages = iq_stages<BS>(), kIqPrefetch = iq_prefetch<BS>();
     constexpr uint32_t RB = kIqStages * HB;  // SSBD blocks in the shared-memory IQ ring (a power of two)
     constexpr uint32_t kStageBytes = (uint32_t)iq_stage_bytes<BS>();
     static_assert((RB & (RB - 1)) == 0 && P0 * HB >= 31 && P0 + 1 + kIqPrefetch + kBufs + 2 <= kIqStages, "IQ ring geometry");
@@ -199,6 +231,8 @@ __global__ void __maxnreg__(104)
     float2* spec = reinterpret_cast<float2*>(smem);
     float2* iq_s = reinterpret_cast<float2*>(smem + spec_bytes<BS>());
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + spec_bytes<BS>() + kIqStages * iq_stage_bytes<BS>());
+    float* lane_rec = reinterpret_cast<float*>(smem + spec_bytes<BS>() + kIqStages * iq_stage_bytes<BS>() + kIqStages * 8);
+    constexpr int REC = lane_rec_floats<BS>(), RSTR = lane_rec_stride<BS>();
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint32_t s0 = blockIdx.x * batches_per_cta;
     const uint32_t s1 = min(n_batches, s0 + batches_per_cta);
@@ -208,10 +242,25 @@ __global__ void __maxnreg__(104)
         for (int i = 0; i < kIqStages; ++i) mbar_init(smem_u32(bars + i), 1);
         fence_mbar_init();
     }
+    for (uint32_t i = t; i < 32u * REC; i += kThreads) {  // lane records: T1[A/4], T2[4] (float2 each), window[A/2]
+        const uint32_t ln = i / REC, f = i % REC;
+        float val;
+        if (f < (uint32_t)(A / 2)) {
+            const float2 w = __ldg(c.twiddle + 32 * (4 * (f >> 1)) + ln);   // q1 = 4a: W_N^(lane 4a), i^(4a) = 1
+            val = (f & 1u) ? w.y : w.x;
+        } else if (f < (uint32_t)(A / 2 + 8)) {
+            const float2 w = __ldg(c.twiddle + 32 * ((f - A / 2) >> 1) + ln);  // q1 = b < 4: W_N^(lane b) i^b
+            val = (f & 1u) ? w.y : w.x;
+        } else {
+            val = __ldg(c.window + 32 * (f - A / 2 - 8) + ln);
+        }
+        lane_rec[ln * RSTR + f] = val;
+    }
     __syncthreads();
 
     if (warp < (uint32_t)kFftWarps) {
         // ================= producers: warp w transforms hops w*HW .. w*HW+HW-1 of every batch =================
+        setmaxnreg_dec<kFftRegs>();
         const uint32_t nb = s1 - s0;
         // local stage l of this CTA holds the slot-relative blocks kbase0 + HB*l .. +HB-1; batch `it` (its own new
         // samples are stage P0 + it) reads stages it .. it + P0
@@ -232,9 +281,7 @@ __global__ void __maxnreg__(104)
         // block b-31 + j1*(32/BS) + lane/BS, sample lane % BS
         long long blk = (long long)p.b0 + (long long)s0 * HB + (long long)warp * HW - 31 + (long long)(lane / BS);
         uint32_t lb = (uint32_t)P0 * HB + warp * HW - 31 + lane / BS;  // the same block, counted from kbase0
-        float wv[A / 2];  // this lane's window taps (constant over the launch)
-#pragma unroll
-        for (int j1 = 0; j1 < A / 2; ++j1) wv[j1] = __ldg(c.window + 32 * j1 + lane);
+        const float4* rec4 = reinterpret_cast<const float4*>(lane_rec + lane * RSTR);
         uint32_t s = 0, waited = 0;
         for (uint32_t it = 0; it < nb; ++it, s = (s + 1 == (uint32_t)kBufs) ? 0u : s + 1) {
             if (t == 0 && it > 0 && it + kIqPrefetch < nb) issue_stage((uint32_t)P0 + it + kIqPrefetch);
@@ -244,28 +291,61 @@ __global__ void __maxnreg__(104)
             }
             float2* wbuf = spec + ((size_t)s * HB + (size_t)warp * HW) * HOP;  // this warp's HW hop buffers
             float2 v[32];
+            float wv[A / 2];  // this lane's window taps
+#pragma unroll
+            for (int j = 0; j < A / 8; ++j) {
+                const float4 f = rec4[(A / 2 + 8) / 4 + j];
+                wv[4 * j] = f.x, wv[4 * j + 1] = f.y, wv[4 * j + 2] = f.z, wv[4 * j + 3] = f.w;
+            }
             // pass 1: lane = j2; per hop an A-point DFT over j1 of u[32 j1 + j2], u = x * window (j1 >= A/2: zero padding)
+            // Common case (warp-uniform): the hop's 32 blocks neither wrap in the shared-memory ring nor reach back
+            // before the slot -> one base pointer, compile-time offsets, no masks.
+            const uint32_t lbw = (lb - lane / BS) & (RB - 1u);  // the warp's first block of this batch in the ring
+            if (lbw + 31u + (uint32_t)HW <= RB && blk - (long long)(lane / BS) >= 0) {
+                const float2* src = iq_s + (size_t)(lbw + lane / BS) * BS + (lane % BS);
 #pragma unroll
-            for (int sub = 0; sub < HW; ++sub) {
+                for (int sub = 0; sub < HW; ++sub)
 #pragma unroll
-                for (int j1 = 0; j1 < A / 2; ++j1) {
-                    const int boff = sub + j1 * (32 / BS);     // block offset of this element from the lane's base block
-                    float2 x = iq_s[(size_t)((lb + boff) & (RB - 1u)) * BS + (lane % BS)];
-                    if (blk + boff < 0) x = make_float2(0.0f, 0.0f);  // zero history before the slot (fresh SSBD)
-                    v[sub * A + j1] = fmul2(x, bc(wv[j1]));
+                    for (int j1 = 0; j1 < A / 2; ++j1)
+                        v[sub * A + j1] = fmul2(src[(sub + j1 * (32 / BS)) * BS], bc(wv[j1]));
+            } else {
+#pragma unroll
+                for (int sub = 0; sub < HW; ++sub) {
+#pragma unroll
+                    for (int j1 = 0; j1 < A / 2; ++j1) {
+                        const int boff = sub + j1 * (32 / BS);     // block offset of this element from the lane's base block
+                        float2 x = iq_s[(size_t)((lb + boff) & (RB - 1u)) * BS + (lane % BS)];
+                        if (blk + boff < 0) x = make_float2(0.0f, 0.0f);  // zero history before the slot (fresh SSBD)
+                        v[sub * A + j1] = fmul2(x, bc(wv[j1]));
+                    }
                 }
             }
             fft_dif_all<A, true>(v);
             if (it >= (uint32_t)kBufs) bar_sync(kBarEmpty + s, kThreads);  // consumers are done with this buffer
-            // twiddle W_N^(j2 q1) * i^q1 and transpose through the hop buffer (rows of 34: conflict-free both ways)
+            // twiddle W_N^(j2 q1) * i^q1 = T1[q1 >> 2] * T2[q1 & 3] and transpose through the hop buffer (rows of 34:
+            // conflict-free both ways)
+            {
+                float2 t1[A / 4], t2[4];
 #pragma unroll
-            for (int sub = 0; sub < HW; ++sub) {
+                for (int j = 0; j < A / 8; ++j) {
+                    const float4 f = rec4[j];
+                    t1[2 * j] = make_float2(f.x, f.y), t1[2 * j + 1] = make_float2(f.z, f.w);
+                }
 #pragma unroll
-                for (int k = 0; k < A; ++k) {
-                    const int q1 = bitrev<A>(k);
-                    const float2 w = __ldg(c.twiddle + 32 * q1 + lane);
-                    const float2 a = v[sub * A + k];
-                    wbuf[sub * HOP + q1 * kRow + lane] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+                for (int j = 0; j < 2; ++j) {
+                    const float4 f = rec4[A / 8 + j];
+                    t2[2 * j] = make_float2(f.x, f.y), t2[2 * j + 1] = make_float2(f.z, f.w);
+                }
+#pragma unroll
+                for (int sub = 0; sub < HW; ++sub) {
+#pragma unroll
+                    for (int k = 0; k < A; ++k) {
+                        const int q1 = bitrev<A>(k);
+                        float2 a = v[sub * A + k];
+                        if (q1 >> 2) a = cmul_pk(a, t1[q1 >> 2].x, t1[q1 >> 2].y);
+                        if (q1 & 3) a = cmul_pk(a, t2[q1 & 3].x, t2[q1 & 3].y);
+                        wbuf[sub * HOP + q1 * kRow + lane] = a;
+                    }
                 }
             }
             __syncwarp();
@@ -282,51 +362,69 @@ __global__ void __maxnreg__(104)
             fft_dif<32, 0, false>(v);
 #pragma unroll
             for (int k = 0; k < 32; ++k) buf[A * bitrev<32>(k) + q1] = v[k];
-            // bins 0..7 again behind bin N-1, so stencils never wrap (bin q1 + A*q2 < 8 <=> q2 == 0 and q1 < 8)
-            if (q1 < 8) buf[N + q1] = v[0];
+            // bins 0..9 again behind bin N-1, so the 12-bin windows (even start) never wrap: bin q1 + A*q2
+            if constexpr (A >= G::kWrap) {
+                if (q1 < (uint32_t)G::kWrap) buf[N + q1] = v[0];
+            } else {
+                buf[N + q1] = v[0];                                                   // q2 = 0
+                if (q1 < (uint32_t)(G::kWrap - A)) buf[N + A + q1] = v[bitrev<32>(1)];  // q2 = 1
+            }
             bar_arrive(kBarFull + s, kThreads);
             blk += HB;
             lb += HB;
         }
     } else {
-        // ================= consumers: thread owns channels tid, tid+256, ... =================
+        // ================= consumers: thread tid owns work item tid (<= 4 neighbouring channels) =================
+        setmaxnreg_inc<kIntRegs>();
+        constexpr int M = kChanItemMembers, T = kChanItemTaps;
+        constexpr int kShift[M] = {0, 0, 1, 2};
         const uint32_t tid = t - kFftThreads;
-        uint32_t off[KC];      // byte offset of the channel's first stencil bin inside a hop buffer
-        float wg[KC][8];       // interpolation weights
-        float2 pinc[KC], R[KC];
-        float sgn[KC], mx[KC];
-        uint32_t ea[KC];       // guard: integer sum of the scaled octet energies of the current segment
+        const bool act = tid < c.n_items;
+        const ChanItem* item = c.items + (act ? tid : 0u);
+        float w[M][T];
+        float2 pinc[M], R[M];
+        float sgn[M], mx[M];
+        uint32_t chn[M], ea[M];  // ea (guard): integer sum of the scaled octet energies of the current segment
+        uint32_t boff;
+        {
+            const float4* q = reinterpret_cast<const float4*>(item);
+            const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+            boff = (uint32_t)__float_as_int(q0.x);
+            chn[0] = (uint32_t)__float_as_int(q1.x), chn[1] = (uint32_t)__float_as_int(q1.y);
+            chn[2] = (uint32_t)__float_as_int(q1.z), chn[3] = (uint32_t)__float_as_int(q1.w);
+            sgn[0] = q2.x, sgn[1] = q2.y, sgn[2] = q2.z, sgn[3] = q2.w;
+            pinc[0] = make_float2(q3.x, q3.y), pinc[1] = make_float2(q3.z, q3.w);
+            pinc[2] = make_float2(q4.x, q4.y), pinc[3] = make_float2(q4.z, q4.w);
+            const float* wp = reinterpret_cast<const float*>(item) + 28;  // w[][] starts at byte 112
 #pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            const uint32_t ch = tid + k * kIntThreads;
-            const float4* kc = reinterpret_cast<const float4*>(c.consts + (ch < p.n_channels ? ch : 0));
-            const float4 k0 = __ldg(kc), k1 = __ldg(kc + 1), k2 = __ldg(kc + 2), k3 = __ldg(kc + 3);
-            off[k] = ((uint32_t)__float_as_int(k0.x) & (uint32_t)(N - 1)) * 8u;
-            sgn[k] = k0.y;
-            wg[k][0] = k1.x, wg[k][1] = k1.y, wg[k][2] = k1.z, wg[k][3] = k1.w;
-            wg[k][4] = k2.x, wg[k][5] = k2.y, wg[k][6] = k2.z, wg[k][7] = k2.w;
-            pinc[k] = make_float2(k3.x, k3.y);
-            R[k] = make_float2(0.0f, 0.0f);
-            mx[k] = 0.0f;
-            ea[k] = 0u;
+            for (int j = 0; j < M; ++j)
+#pragma unroll
+                for (int i = 0; i < T; ++i) w[j][i] = __ldg(wp + j * T + i);
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                if (!act) chn[j] = 0xffffffffu;
+                R[j] = make_float2(0.0f, 0.0f);
+                mx[j] = 0.0f;
+                ea[j] = 0u;
+            }
         }
         // R = P_c[128 a] * rot_c from the exact recurrence (anchor table), then R <- R * phase_inc per hop
-        auto anchor = [&](int k, uint32_t a) {
-            const uint32_t ch = tid + k * kIntThreads;
-            const float2 P = __ldg(c.anchors + (size_t)a * c.anchor_stride + ch);
-            const float4 k0 = __ldg(reinterpret_cast<const float4*>(c.consts + ch));  // rot = (z, w); needed here only
-            return cmul_fix(P, make_float2(k0.z, k0.w));
+        auto anchor = [&](int j, uint32_t a) {
+            const float2 P = __ldg(c.anchors + (size_t)a * c.anchor_stride + chn[j]);
+            const float2 rot = __ldg(reinterpret_cast<const float2*>(item) + 10 + j);  // rot[][] starts at byte 80
+            return cmul_fix(P, rot);
         };
         const uint32_t bb0 = p.b0 + s0 * HB;
         {   // a run that starts between two anchors replays the steps from the anchor before it: same bits as a run
             // that came through them
             const uint32_t a0 = bb0 / kChanAnchorHops, n_replay = bb0 % kChanAnchorHops;
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if (tid + k * kIntThreads >= p.n_channels) continue;
-                float2 r = anchor(k, a0);
-                for (uint32_t j = 0; j < n_replay; ++j) r = cmul_fix(r, pinc[k]);
-                R[k] = r;
+            for (int j = 0; j < M; ++j) {
+                if (chn[j] == 0xffffffffu) continue;
+                float2 r = anchor(j, a0);
+#pragma unroll 1
+                for (uint32_t i = 0; i < n_replay; ++i) r = cmul_fix(r, pinc[j]);
+                R[j] = r;
             }
         }
         // dynamic-range guard statistics (cwsl_guard.cu): per segment max|y| and an integer energy sum
@@ -336,19 +434,19 @@ __global__ void __maxnreg__(104)
         float s2 = guard ? __ldg(c.seg_scale + cur_seg) : 0.0f;
         auto flush = [&]() {
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const uint32_t ch = tid + k * kIntThreads;
-                if (ch >= p.n_channels) continue;
-                const unsigned bits = __float_as_uint(mx[k]);
+            for (int j = 0; j < M; ++j) {
+                const uint32_t ch = chn[j];
+                if (ch == 0xffffffffu) continue;
+                const unsigned bits = __float_as_uint(mx[j]);
                 if (guard) {
                     const size_t i = (size_t)cur_seg * c.stat_stride + ch;
                     if (bits != 0u) atomicMax(c.seg_max + i, bits);
-                    if (ea[k] != 0u) atomicAdd(c.seg_energy + i, ea[k]);
+                    if (ea[j] != 0u) atomicAdd(c.seg_energy + i, ea[j]);
                 } else if (bits != 0u && bits > __ldcg(p.maxbits + ch)) {
                     atomicMax(p.maxbits + ch, bits);
                 }
-                mx[k] = 0.0f;
-                ea[k] = 0u;
+                mx[j] = 0.0f;
+                ea[j] = 0u;
             }
         };
         uint32_t s = 0;
@@ -356,8 +454,8 @@ __global__ void __maxnreg__(104)
             const uint32_t bb = p.b0 + i * HB;
             if (i != s0 && (bb % kChanAnchorHops) == 0u) {
 #pragma unroll
-                for (int k = 0; k < KC; ++k)
-                    if (tid + k * kIntThreads < p.n_channels) R[k] = anchor(k, bb / kChanAnchorHops);
+                for (int j = 0; j < M; ++j)
+                    if (chn[j] != 0xffffffffu) R[j] = anchor(j, bb / kChanAnchorHops);
             }
             if (bb >= next_seg_b) {  // (segments are multiples of 32 hops: a batch never straddles two)
                 flush();
@@ -366,61 +464,64 @@ __global__ void __maxnreg__(104)
                 s2 = __ldg(c.seg_scale + cur_seg);
             }
             bar_sync(kBarFull + s, kThreads);
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if (tid + k * kIntThreads >= p.n_channels) continue;
+            if (act) {
 #pragma unroll 1
                 for (int oct = 0; oct < HB / 8; ++oct) {  // eight hops at a time: one 32-byte store per channel
                     const uint32_t b8 = bb + 8 * oct;
-                    const unsigned char* base = smem + ((size_t)s * HB + 8 * oct) * HOP * 8 + off[k];
-                    float out[8];
+                    const unsigned char* base = smem + ((size_t)s * HB + 8 * oct) * HOP * 8 + boff;
+                    float out[M][8];
 #pragma unroll
                     for (int h = 0; h < 8; ++h) {
                         const float4* bins = reinterpret_cast<const float4*>(base + (size_t)h * HOP * 8);
-                        float2 acc = make_float2(0.0f, 0.0f);
+                        float2 bn[kChanItemBins];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                        for (int q = 0; q < kChanItemBins / 2; ++q) {
                             const float4 two = bins[q];
-                            acc = ffma2(make_float2(two.x, two.y), bc(wg[k][2 * q]), acc);
-                            acc = ffma2(make_float2(two.z, two.w), bc(wg[k][2 * q + 1]), acc);
+                            bn[2 * q] = make_float2(two.x, two.y);
+                            bn[2 * q + 1] = make_float2(two.z, two.w);
                         }
-                        const float2 r = R[k];
-                        // audio[b] = {+Re, -Im*sign, -Re, +Im*sign}[b & 3] of acc*R; b8 is a multiple of 4
-                        float o;
-                        if ((h & 3) == 0) o = __fmaf_rn(acc.x, r.x, -__fmul_rn(acc.y, r.y));
-                        else if ((h & 3) == 1) o = -__fmaf_rn(acc.x, r.y, __fmul_rn(acc.y, r.x)) * sgn[k];
-                        else if ((h & 3) == 2) o = -__fmaf_rn(acc.x, r.x, -__fmul_rn(acc.y, r.y));
-                        else o = __fmaf_rn(acc.x, r.y, __fmul_rn(acc.y, r.x)) * sgn[k];
-                        out[h] = o;
-                        R[k] = cmul_fix(r, pinc[k]);
+#pragma unroll
+                        for (int j = 0; j < M; ++j) {
+                            float2 acc = fmul2(bn[kShift[j]], bc(w[j][0]));
+#pragma unroll
+                            for (int q = 1; q < T; ++q) acc = ffma2(bn[kShift[j] + q], bc(w[j][q]), acc);
+                            const float2 r = R[j];
+                            // audio[b] = {+Re, -Im*sign, -Re, +Im*sign}[b & 3] of acc*R; b8 is a multiple of 4
+                            float o;
+                            if ((h & 3) == 0) o = __fmaf_rn(acc.x, r.x, -__fmul_rn(acc.y, r.y));
+                            else if ((h & 3) == 1) o = -__fmaf_rn(acc.x, r.y, __fmul_rn(acc.y, r.x)) * sgn[j];  // (x * +-1: exact)
+                            else if ((h & 3) == 2) o = -__fmaf_rn(acc.x, r.x, -__fmul_rn(acc.y, r.y));
+                            else o = __fmaf_rn(acc.x, r.y, __fmul_rn(acc.y, r.x)) * sgn[j];
+                            out[j][h] = o;
+                            R[j] = cmul_fix(r, pinc[j]);
+                        }
                     }
-                    float* dst = p.audio + (size_t)(tid + k * kIntThreads) * p.af_stride + b8;
-                    float e8 = 0.0f;
-                    if (b8 + 8 <= p.b1 && (b8 & 7u) == 0) {  // whole octet, 32-byte aligned row segment
-                        stg256(dst, out);
-                        float m = mx[k];
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) {
-                            m = fmaxf(m, fabsf(out[h]));
-                            e8 = __fmaf_rn(out[h], out[h], e8);
-                        }
-                        mx[k] = m;
-                    } else {
+                    for (int j = 0; j < M; ++j) {
+                        if (chn[j] == 0xffffffffu) continue;
+                        float* dst = p.audio + (size_t)chn[j] * p.af_stride + b8;
+                        float e8 = 0.0f;
+                        if (b8 + 8 <= p.b1) {  // whole octet, 32-byte aligned row segment
+                            stg256(dst, out[j]);
+                            float m = mx[j];
 #pragma unroll
-                        for (int h4 = 0; h4 < 8; h4 += 4) {
-                            if (b8 + h4 < p.b1) {  // b1 is a multiple of 4
-                                *reinterpret_cast<float4*>(dst + h4) = make_float4(out[h4], out[h4 + 1], out[h4 + 2], out[h4 + 3]);
+                            for (int h = 0; h < 8; ++h) {
+                                m = fmaxf(m, fabsf(out[j][h]));
+                                e8 = __fmaf_rn(out[j][h], out[j][h], e8);
+                            }
+                            mx[j] = m;
+                        } else if (b8 < p.b1) {  // b1 is a multiple of 4: the first quartet only
+                            *reinterpret_cast<float4*>(dst) = make_float4(out[j][0], out[j][1], out[j][2], out[j][3]);
 #pragma unroll
-                                for (int h = h4; h < h4 + 4; ++h) {
-                                    mx[k] = fmaxf(mx[k], fabsf(out[h]));
-                                    e8 = __fmaf_rn(out[h], out[h], e8);
-                                }
+                            for (int h = 0; h < 4; ++h) {
+                                mx[j] = fmaxf(mx[j], fabsf(out[j][h]));
+                                e8 = __fmaf_rn(out[j][h], out[j][h], e8);
                             }
                         }
+                        // scaled so that the guard's keep-threshold is 128 per hop on average; the integer sum is exact,
+                        // hence independent of how the segment is spread over CTAs and launches
+                        if (guard) ea[j] += __float2uint_rz(fminf(__fmul_rn(e8, s2), 1048576.0f));
                     }
-                    // scaled so that the guard's keep-threshold is 128 per hop on average; the integer sum is exact,
-                    // hence independent of how the segment is spread over CTAs and launches
-                    if (guard) ea[k] += __float2uint_rz(fminf(__fmul_rn(e8, s2), 1048576.0f));
                 }
             }
             if (i + kBufs < s1) bar_arrive(kBarEmpty + s, kThreads);  // (nobody waits for the last ones)
@@ -445,10 +546,10 @@ cudaError_t prepare(const void* kern, size_t smem_bytes, int* sms) {
     return cudaSuccess;
 }
 
-template <int BS, int KC>
-cudaError_t launch_t(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
+template <int BS>
+cudaError_t launch_bs(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
     constexpr int HB = ChanGeo<BS>::kHB;
-    auto kern = demod_chan_kernel<BS, KC>;
+    auto kern = demod_chan_kernel<BS>;
     int sms = 0;
     cudaError_t e = prepare(reinterpret_cast<const void*>(kern), chan_smem_bytes<BS>(), &sms);
     if (e != cudaSuccess) return e;
@@ -460,22 +561,10 @@ cudaError_t launch_t(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) 
     return cudaGetLastError();
 }
 
-template <int BS>
-cudaError_t launch_bs(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
-    switch ((p.n_channels + kIntThreads - 1) / kIntThreads) {
-        case 1: return launch_t<BS, 1>(p, c, s);
-        case 2: return launch_t<BS, 2>(p, c, s);
-        case 3: return launch_t<BS, 3>(p, c, s);
-        default: return launch_t<BS, 4>(p, c, s);
-    }
-}
-
 }  // namespace
 
-uint32_t chan_max_channels() { return kChanMaxChannels; }
-
 cudaError_t launch_demod_chan(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s) {
-    if (c.taps != kChanTaps || p.n_channels == 0 || p.n_channels > kChanMaxChannels || p.ring_blocks < 64 ||
+    if (p.n_channels == 0 || c.n_items == 0 || c.n_items > kChanMaxItems || !c.items || p.ring_blocks < 64 ||
         (p.b0 & 31u) || (p.b1 & 3u) || (p.af_stride & 7u) || !c.anchors ||
         (c.seg_blocks != 0u && (p.b0 % c.seg_blocks != 0u || (c.seg_blocks & 31u) || !c.seg_max || !c.seg_energy || !c.seg_scale)))
         return cudaErrorInvalidValue;

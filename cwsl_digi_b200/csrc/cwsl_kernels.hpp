@@ -68,24 +68,33 @@ struct FastIndirect {
 };
 
 // Extra inputs of the STFT channelizer kernel (cwsl_chan.cu); tables from cwsl_tables.hpp chan_*.
-constexpr int kChanTaps = 8;                   // stencil bins per channel: Kaiser-Bessel kernel of width 7 on an even-aligned stencil
-constexpr int kChanKernelWidth = 7;
-constexpr uint32_t kChanMaxChannels = 1024;    // per launch (each interpolation thread keeps <= 4 channels in registers)
+constexpr int kChanTaps = 8;                   // stencil bins per channel of the host-side description (cwsl_stft_channel)
+constexpr int kChanKernelWidth = 7;            // Kaiser-Bessel interpolation kernel: support of 7 grid bins
 constexpr uint32_t kChanAnchorHops = 128;      // the exact phase recurrence is re-read every 128 hops (slot-relative)
-struct alignas(16) ChanConst {   // per-channel constants, four 16-byte loads
-    int q0;           // first grid bin of the interpolation stencil, even (bins are taken mod 1024)
-    float sign;       // +1 USB / -1 LSB
-    float rot[2];     // e^{-i 240 w_c}
-    float wgt[kChanTaps];  // real interpolation weights of bins q0 .. q0+7
-    float pinc[2];    // the reference's float phase_inc (per-hop NCO step between phase-table anchors)
-    float pad[2];
+// Interpolation work item: up to 4 channels that are neighbours on the FFT grid read ONE 12-bin window; member j takes
+// the 9 bins shift[j] .. shift[j]+8 of it, shift = {0,0,1,2} (cwsl_tables.hpp chan_items). One item per interpolation
+// thread, held in registers for the whole launch. Neighbouring items start ~4 bins = two 16-byte bank groups apart, so
+// the host deals the items out over the threads such that the eight lanes of every quarter-warp start in eight different
+// bank groups (cwsl_tables.hpp chan_item_order): their LDS.128 of the window are then conflict-free.
+constexpr int kChanItemMembers = 4, kChanItemTaps = 9, kChanItemBins = 12;
+constexpr uint32_t kChanMaxItems = 256;        // per launch
+struct alignas(16) ChanItem {                  // 256 bytes, sixteen 16-byte loads
+    uint32_t bin_off;                          // byte offset of the window's first bin in a hop buffer: (e mod N) * 8
+    uint32_t n_members;
+    uint32_t pad0[2];
+    uint32_t ch[kChanItemMembers];             // channel index in the slot group, 0xffffffff: empty slot
+    float sign[kChanItemMembers];              // +1 USB / -1 LSB
+    float pinc[kChanItemMembers][2];           // the reference's float phase_inc (per-hop NCO step between anchors)
+    float rot[kChanItemMembers][2];            // e^{-i 240 w_c}
+    float w[kChanItemMembers][kChanItemTaps];  // real interpolation weights, exact zeros outside the kernel's support
 };
+static_assert(sizeof(ChanItem) == 256, "ChanItem layout");
 struct ChanLaunch {
     const float* window = nullptr;    // [512]  taps / psihat((j-256)/1024)
     const float2* twiddle = nullptr;  // [32][32] W1024^(j2*q1) * i^q1 at [q1*32 + j2]
-    const ChanConst* consts = nullptr;  // [n_channels]
-    int taps = kChanTaps;
-    // P_c[128 a] of the exact float recurrence, [anchor][channel] so that a warp reads 256 contiguous bytes
+    const ChanItem* items = nullptr;  // [n_items]
+    uint32_t n_items = 0;             // <= kChanMaxItems
+    // P_c[128 a] of the exact float recurrence, [anchor][channel]
     const float2* anchors = nullptr;
     uint32_t anchor_stride = 0;       // channels per anchor row (the whole slot group)
     // Dynamic-range guard statistics per (segment of this launch, channel); seg_blocks == 0: guard off, max|x| goes
@@ -125,7 +134,8 @@ cudaError_t launch_demod_exact_gather(const DemodLaunch& p, cudaStream_t s);  //
 // FAST: p.b0 must be a multiple of fast_seg_blocks(tiles_per_seg) (segments sit at fixed slot-relative positions).
 // ind.items != nullptr: the channels come from the guard's device-resident work list (persistent grid).
 cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, const FastIndirect& ind, cudaStream_t s);
-// STFT channelizer (<= kChanMaxChannels channels per launch); p.b0 must be a multiple of 32
+// STFT channelizer (<= kChanMaxItems work items per launch; DemodLaunch names the whole slot group); p.b0 must be a
+// multiple of 32
 cudaError_t launch_demod_chan(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s);
 // P_c[spacing * a] gathered from the full phase tables into [n_anchor][n_channels]
 cudaError_t launch_phase_anchors(const float2* const* phase, float2* anchors, uint32_t n_channels, uint32_t n_anchor,

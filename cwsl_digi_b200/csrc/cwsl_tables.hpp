@@ -9,6 +9,7 @@
 // tests/test_tables.py pins them bit-for-bit against oracle/_ref (the reference's own headers).
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstddef>
@@ -163,6 +164,125 @@ inline ChanChannel chan_channel(const SsbdGeometry& g, const NcoTables& t, int w
     const double a = -omega * (double)(g.filt_order - g.block_size - g.filt_order / 2);
     c.rot = std::complex<float>((float)std::cos(a), (float)std::sin(a));
     return c;
+}
+
+// ---- interpolation work items of the channelizer kernel (cwsl_chan.cu) ----------------------------------------
+// The kernel reads a channel's frequency off the FFT grid with the bins of the kernel's support [a, a+6],
+// a = ceil(nu - width/2). Channels that are neighbours on the grid share most of those bins, so the kernel works on
+// ITEMS of up to 4 channels ("members") that read ONE 12-bin window (even first bin e) from shared memory:
+// member j uses the 9 bins e + shift[j] ... e + shift[j] + 8 with shift = {0, 0, 1, 2} (compile-time register
+// indices), weights outside the kernel's support are exact zeros. A member fits slot j iff shift[j] <= a - e <=
+// shift[j] + 2. Channels are taken in ascending grid position and packed greedily; any channel set is legal (a
+// channel that fits no open slot starts a new item), a regular grid of 130 ... 190 Hz spacing fills all four slots.
+// The result of a channel does not depend on how it was grouped: its non-zero weights meet the same bins in the same
+// (ascending) order, and a fused multiply-add with an exact-zero weight is the identity.
+constexpr int kItemMembers = 4, kItemTaps = 9, kItemBins = 12;
+constexpr int kItemShift[kItemMembers] = {0, 0, 1, 2};
+struct ChanItemHost {
+    int e = 0;                              // first bin of the window (even; may be negative: bins are taken mod N)
+    int n = 0;                              // members in use (slots may stay empty in between)
+    int ch[kItemMembers] = {-1, -1, -1, -1};  // channel index in the slot group, -1: empty slot
+    float w[kItemMembers][kItemTaps] = {};
+    std::complex<float> rot[kItemMembers];
+};
+
+struct ChanPos {  // grid position of one channel: nu in [0, N) bins, support start a, rotation e^{-i 240 w}
+    double nu = 0;
+    int a = 0;
+    std::complex<float> rot;
+};
+inline ChanPos chan_position(const SsbdGeometry& g, const NcoTables& t, int width) {
+    double theta = std::atan2((double)t.phase_inc.imag(), (double)t.phase_inc.real());
+    const double nominal = (double)t.phase_delta * g.block_size;
+    theta += 2.0 * kPi * std::round((nominal - theta) / (2.0 * kPi));
+    const double omega = theta / g.block_size;
+    const double n = chan_grid(g);
+    ChanPos p;
+    p.nu = std::fmod(-omega * n / (2.0 * kPi), n);
+    if (p.nu < 0) p.nu += n;
+    p.a = (int)std::ceil(p.nu - width / 2.0);
+    const double ang = -omega * (double)(g.filt_order - g.block_size - g.filt_order / 2);
+    p.rot = std::complex<float>((float)std::cos(ang), (float)std::sin(ang));
+    return p;
+}
+
+inline std::vector<ChanItemHost> chan_items(const SsbdGeometry& g, const std::vector<NcoTables>& nco, int width) {
+    const ChanKernel k(width);
+    std::vector<ChanPos> pos(nco.size());
+    std::vector<int> order(nco.size());
+    for (size_t c = 0; c < nco.size(); ++c) {
+        pos[c] = chan_position(g, nco[c], width);
+        order[c] = (int)c;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pos[x].nu < pos[y].nu; });
+    std::vector<ChanItemHost> items;
+    int next_slot = kItemMembers;  // no item open
+    for (int c : order) {
+        const ChanPos& p = pos[c];
+        int slot = -1;
+        if (!items.empty())
+            for (int j = next_slot; j < kItemMembers; ++j) {
+                const int d = p.a - items.back().e;
+                if (d >= kItemShift[j] && d <= kItemShift[j] + 2) {
+                    slot = j;
+                    break;
+                }
+            }
+        if (slot < 0) {
+            ChanItemHost it;
+            it.e = p.a - (p.a & 1);  // (two's complement: also the next lower even number for negative a)
+            items.push_back(it);
+            slot = 0;
+        }
+        ChanItemHost& it = items.back();
+        it.ch[slot] = c;
+        it.rot[slot] = p.rot;
+        for (int i = 0; i < kItemTaps; ++i) it.w[slot][i] = (float)k.psi(p.nu - (it.e + kItemShift[slot] + i));
+        it.n = slot + 1;
+        next_slot = slot + 1;
+    }
+    return items;
+}
+
+// Thread placement of the items of each launch (<= per_launch items, one per interpolation thread). The eight lanes of
+// a quarter-warp read 16 bytes each at their window start + 16 q; that is conflict-free iff their starts fall into
+// eight different 16-byte bank groups, i.e. (e/2) mod 8 are all different (the same shift q for every lane keeps them
+// different). Items are dealt out per launch, quarter-warp by quarter-warp: each of its eight places goes to the
+// residue class that is furthest behind an even spread over the quarter-warps still to fill, so a class with more than
+// its share costs single 2-way conflicts spread over the launch instead of one fully serialised quarter-warp at the end.
+inline std::vector<ChanItemHost> chan_item_order(const std::vector<ChanItemHost>& items, int grid_bins, size_t per_launch) {
+    std::vector<ChanItemHost> out;
+    out.reserve(items.size());
+    for (size_t i0 = 0; i0 < items.size(); i0 += per_launch) {
+        const size_t n = std::min(per_launch, items.size() - i0);
+        std::vector<std::vector<size_t>> cls(8);
+        for (size_t i = i0 + n; i-- > i0;) {  // (reversed, so that pop_back hands them out in ascending order)
+            const int e = ((items[i].e % grid_bins) + grid_bins) % grid_bins;
+            cls[(e / 2) % 8].push_back(i);
+        }
+        const size_t quarters = (n + 7) / 8;
+        for (size_t q = 0; q < quarters; ++q) {
+            const long left = (long)(quarters - q);
+            int taken[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const size_t places = std::min<size_t>(8, n - 8 * q);
+            for (size_t k = 0; k < places; ++k) {
+                int best = -1;
+                long best_pri = 0;
+                for (int r = 0; r < 8; ++r) {
+                    if (cls[r].empty()) continue;
+                    const long pri = (long)cls[r].size() + taken[r] - (long)taken[r] * left;  // = count at quarter start - taken * left
+                    if (best < 0 || pri > best_pri) {
+                        best = r;
+                        best_pri = pri;
+                    }
+                }
+                out.push_back(items[cls[best].back()]);
+                cls[best].pop_back();
+                ++taken[best];
+            }
+        }
+    }
+    return out;
 }
 
 inline size_t af_size(double period_s) {  // source/Instance.cpp:149

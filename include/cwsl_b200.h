@@ -89,6 +89,15 @@ int cwsl_build_tables(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, f
 int cwsl_stft_tables(uint32_t sample_rate, float* window, float* twiddle);
 int cwsl_stft_channel(uint32_t sample_rate, int32_t demod_freq_hz, int is_usb, int32_t* q0, float* wgt,
                       float* rot);
+/* How the channelizer kernel groups a channel set (no device needed): channels that are neighbours on the FFT grid are
+ * packed, in ascending grid position, into work items of <= 4 members that read one 12-bin window starting at the
+ * (even) bin first_bin[i]; member j uses the 9 bins first_bin[i] + shift[j] ... + 8, shift = {0,0,1,2}, with the real
+ * weights weights[i][j][0..8] (exact zeros outside the interpolation kernel's support, so every channel meets the
+ * same non-zero weights on the same bins as in cwsl_stft_channel). channels[i][j] = index into demod_freq_hz, or -1
+ * for an empty slot. Arrays are sized for n items (the worst case: no two channels share a window); *n_items returns
+ * how many were built. */
+int cwsl_stft_items(uint32_t sample_rate, const int32_t* demod_freq_hz, const int* is_usb, uint32_t n,
+                    int32_t* first_bin, int32_t* channels, float* weights, uint32_t* n_items);
 
 /* (period + 5 s) * 12000: length of one decoder's audio buffer, source/Instance.cpp:149. */
 size_t cwsl_af_size(double period_s);

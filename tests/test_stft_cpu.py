@@ -105,3 +105,46 @@ def test_stft_math_at_the_other_receiver_rates(cw, port, fs, freq):
     assert resid_db(got, o["raw"][:wi]) <= -110.0
     q = np.trunc(got * np.float32(o["factor"]) + np.float32(0.5)).astype(np.int32)
     assert np.abs(q - o["i16"][:wi].astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("fs", [192000, 96000, 48000])
+def test_work_items_cover_every_channel_with_its_own_stencil(cw, fs):
+    """cwsl_stft_items (the grouping the channelizer kernel runs on): every channel sits in exactly one slot, its nine
+    item weights are its own eight stencil weights at the same absolute bins and exact zeros elsewhere, the window
+    starts on an even bin and a regular grid fills (nearly) all four slots -- for the stress sweep's regular grid, for
+    random channel sets and for a grid far denser than the FFT's."""
+    N, _, _ = geo(fs)
+    half = fs // 2
+    rng = np.random.default_rng(5)
+    sets = {
+        "stress": np.unique((-half + np.round(np.arange(1024) * (fs - 6000.0) / 1023)).astype(np.int32))[:1024],
+        "random": rng.integers(-half, half - 6000, 300).astype(np.int32),
+        "dense": (-20000 + 37 * np.arange(500)).astype(np.int32),
+        "single": np.array([-26000 if fs == 192000 else -6000], np.int32),
+    }
+    for name, freqs in sets.items():
+        usb = (np.arange(freqs.size) % 3 != 0).astype(np.int32) if name == "random" else np.ones(freqs.size, np.int32)
+        legal = np.array([abs(int(f)) <= half and abs(int(f) + (6000 if u else -6000)) <= half for f, u in zip(freqs, usb)])
+        freqs, usb = freqs[legal], usb[legal]
+        it = cw.stft_items(fs, freqs, usb)
+        members = it["channels"][it["channels"] >= 0]
+        assert sorted(members.tolist()) == list(range(freqs.size)), name
+        assert (it["first_bin"] % 2 == 0).all()
+        for i in range(it["first_bin"].size):
+            for j in range(4):
+                c = it["channels"][i, j]
+                if c < 0:
+                    assert not it["weights"][i, j].any()
+                    continue
+                ch = cw.stft_channel(fs, int(freqs[c]), bool(usb[c]))
+                want = np.zeros(12 + 16, np.float32)          # absolute bins first_bin-8 ... first_bin+19
+                d = (ch["q0"] - it["first_bin"][i]) % N
+                d = d - N if d > N // 2 else d
+                want[8 + d: 8 + d + 8] = ch["wgt"]
+                got = np.zeros_like(want)
+                got[8 + it["shift"][j]: 8 + it["shift"][j] + 9] = it["weights"][i, j]
+                assert np.array_equal(got, want), (name, i, j)
+        if name == "stress" and fs == 192000:              # 0.97 bins between neighbours: every slot is used
+            assert it["first_bin"].size == freqs.size // 4 == 256   # = one launch of the kernel
+        if name == "single":
+            assert it["first_bin"].size == 1
