@@ -776,8 +776,10 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, cons
 // IEEE flags. Samples past write_index are the zero tail: (int16)(0*factor + 0.5f) = 0.
 // ------------------------------------------------------------------------------------------
 // Each thread converts kQuantVec groups of 8 samples, all of its loads issued before the first conversion: the pass
-// is pure HBM traffic, and it usually runs in the one CTA slot per SM that the STFT demodulator of the NEXT receiver
-// leaves free, so bytes in flight per thread are what make it fast.
+// is pure HBM traffic (0.19 ms per 1024-channel FT8 slot = 6.5 TB/s). It runs on the receiver's post stream: under the
+// FMA-bound FAST / EXACT demodulation of the next receiver, after the STFT channelizer (whose 512 x 120 registers leave
+// no room for a second CTA; a 32-register row-walking variant with L2 prefetch that did fit beside it stretched the
+// channelizer by more than it saved: 0.90 instead of 0.78 ms per receiver, measured).
 constexpr int kQuantThreads = 128, kQuantVec = 4;
 __global__ void __launch_bounds__(kQuantThreads) quantise_kernel(QuantLaunch p) {
     const uint32_t c = blockIdx.y;
