@@ -776,12 +776,15 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, cons
 // IEEE flags. Samples past write_index are the zero tail: (int16)(0*factor + 0.5f) = 0.
 // ------------------------------------------------------------------------------------------
 // Each thread converts kQuantVec groups of 8 samples, all of its loads issued before the first conversion: the pass
-// is pure HBM traffic (0.19 ms per 1024-channel FT8 slot = 6.5 TB/s). It runs on the receiver's post stream: under the
-// FMA-bound FAST / EXACT demodulation of the next receiver, after the STFT channelizer (whose 512 x 120 registers leave
-// no room for a second CTA; a 32-register row-walking variant with L2 prefetch that did fit beside it stretched the
-// channelizer by more than it saved: 0.90 instead of 0.78 ms per receiver, measured).
-constexpr int kQuantThreads = 128, kQuantVec = 4;
-__global__ void __launch_bounds__(kQuantThreads) quantise_kernel(QuantLaunch p) {
+// is pure HBM traffic (0.19 ms per 1024-channel FT8 slot = 6.5 TB/s). It runs on the receiver's post stream under the
+// demodulation of the next receiver. 128 threads x 32 registers = 4096 registers per CTA is exactly what the STFT
+// channelizer (512 x 120) leaves free on an SM, so one CTA of this kernel runs beside it: 0.745 instead of 0.788 ms
+// per receiver in the 64-receiver bench; alone, the 32-register shape (two groups per thread) is as fast as the
+// 48-register one (four groups). (A row-walking variant with prefetch.global.L2 stretched the channelizer by more than
+// it saved, 0.90 ms per receiver: rejected.)
+constexpr int kQuantThreads = 128, kQuantVec = 2, kQuantRegs = 32;
+template <int kQuantVec, int kRegs>
+__global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
     const uint32_t c = blockIdx.y;
     const float maxv = __uint_as_float(p.maxbits[c]);
     float factor = __fdiv_rn(32767.0f, __fadd_rn(maxv, 1.0f));
@@ -837,9 +840,9 @@ __global__ void __launch_bounds__(kQuantThreads) quantise_kernel(QuantLaunch p) 
 
 cudaError_t launch_quantise(const QuantLaunch& p, cudaStream_t s) {
     if (p.n_channels == 0 || p.af_size == 0) return cudaSuccess;
-    const uint32_t per_cta = kQuantThreads * 8u * kQuantVec;
+    const uint32_t per_cta = kQuantThreads * 8u * (uint32_t)kQuantVec;
     dim3 grid((p.af_size + per_cta - 1) / per_cta, p.n_channels);
-    quantise_kernel<<<grid, kQuantThreads, 0, s>>>(p);
+    quantise_kernel<kQuantVec, kQuantRegs><<<grid, kQuantThreads, 0, s>>>(p);
     return cudaGetLastError();
 }
 
