@@ -75,6 +75,13 @@ struct AnchorEntry {
     int refs = 0;
 };
 std::map<std::vector<PhaseKey>, AnchorEntry> g_anchor_cache;
+// Scratch of the STFT guard's indirect FAST launches (phases replayed from the anchors, cwsl_kernels.hpp FastIndirect):
+// one per (device, stream) -- launches on one stream are serialised, so every receiver queued on it shares the buffer.
+struct ScratchEntry {
+    float2* p = nullptr;
+    int refs = 0;
+};
+std::map<std::pair<int, cudaStream_t>, ScratchEntry> g_fast_scratch;
 
 // Managed hand-off buffers (cwsl_host_alloc): pinned, zero-initialised, and only ever written by
 // cwsl_rx_end_slot, so the library knows which columns of a destination can hold non-zero data and
@@ -108,7 +115,9 @@ struct Group {
     std::vector<int> pending_remove;
     // device
     float2* d_tone = nullptr;
-    const float2** d_phase = nullptr;
+    const float2** d_phase = nullptr;   // [C] -> full phase tables; entries are filled by ensure_phase_tables() (EXACT / FAST launches)
+    bool have_phase_tables = false;
+    float2* d_pinc = nullptr;           // [C] the reference's float phase_inc per channel
     float* d_sign = nullptr;
     float* d_scale = nullptr;
     unsigned* d_maxbits = nullptr;
@@ -171,6 +180,8 @@ struct cwsl_rx {
     static constexpr uint64_t kFences = 64;
     cudaEvent_t fence_ev[kFences] = {};
     uint64_t fence_next = 1;  // token of the next fence; token t lives in fence_ev[t % kFences]
+    float2* fast_scratch = nullptr;          // see g_fast_scratch; referenced for `fast_scratch_stream`
+    cudaStream_t fast_scratch_stream = nullptr;
     double guard_db = 0;  // STFT dynamic-range guard threshold (dB below the band's mean power); <= 0: off
     // timing
     bool timing = false;
@@ -221,6 +232,7 @@ void release_anchor_ref(Group& g) {  // g_mu held
 void free_group_device(Group& g) {
     cudaFree(g.d_tone);
     cudaFree((void*)g.d_phase);
+    cudaFree(g.d_pinc);
     cudaFree(g.d_sign);
     cudaFree(g.d_scale);
     cudaFree(g.d_maxbits);
@@ -239,6 +251,7 @@ void free_group_device(Group& g) {
     g.d_chan = nullptr;
     g.d_tone = nullptr;
     g.d_phase = nullptr;
+    g.d_pinc = nullptr;
     g.d_sign = g.d_scale = g.d_factor = g.d_maxval = g.d_audio = g.d_seg_scale = nullptr;
     g.d_maxbits = g.d_seg_max = g.d_seg_energy = g.d_n_items = nullptr;
     g.d_sel = nullptr;
@@ -249,13 +262,15 @@ void free_group_device(Group& g) {
     g.committed = false;
     std::lock_guard<std::mutex> lk(g_mu);
     release_anchor_ref(g);
-    for (const PhaseKey& k : g.phase_keys) {
-        auto it = g_phase_cache.find(k);
-        if (it != g_phase_cache.end() && --it->second.refs <= 0) {
-            cudaFree(it->second.table);
-            g_phase_cache.erase(it);
+    if (g.have_phase_tables)
+        for (const PhaseKey& k : g.phase_keys) {
+            auto it = g_phase_cache.find(k);
+            if (it != g_phase_cache.end() && --it->second.refs <= 0) {
+                cudaFree(it->second.table);
+                g_phase_cache.erase(it);
+            }
         }
-    }
+    g.have_phase_tables = false;
     g.phase_keys.clear();
 }
 
@@ -347,9 +362,10 @@ int commit_group_impl(cwsl_rx* rx, Group& g) {
     const uint32_t BS = rx->geo.block_size;
     g.af_stride = (g.af_size + 7) / 8 * 8;
     g.tiles = cwsl::fast_tiles_per_seg(C);
-    std::vector<float2> tone((size_t)C * BS);
+    std::vector<float2> tone((size_t)C * BS), pinc(C);
     std::vector<float> sign(C), scale(C);
     for (uint32_t c = 0; c < C; ++c) {
+        pinc[c] = make_float2(g.ch[c].nco.phase_inc.real(), g.ch[c].nco.phase_inc.imag());
         for (uint32_t m = 0; m < BS; ++m)
             tone[(size_t)c * BS + m] = make_float2(g.ch[c].nco.tone[m].real(), g.ch[c].nco.tone[m].imag());
         sign[c] = g.ch[c].nco.sign;
@@ -357,6 +373,8 @@ int commit_group_impl(cwsl_rx* rx, Group& g) {
     }
     CK(cudaMalloc(&g.d_tone, tone.size() * sizeof(float2)));
     CK(cudaMalloc((void**)&g.d_phase, C * sizeof(float2*)));
+    CK(cudaMemsetAsync((void*)g.d_phase, 0, C * sizeof(float2*), rx->stream));
+    CK(cudaMalloc(&g.d_pinc, C * sizeof(float2)));
     CK(cudaMalloc(&g.d_sign, C * sizeof(float)));
     CK(cudaMalloc(&g.d_scale, C * sizeof(float)));
     CK(cudaMalloc(&g.d_maxbits, C * sizeof(unsigned)));
@@ -366,6 +384,7 @@ int commit_group_impl(cwsl_rx* rx, Group& g) {
     CK(cudaMalloc(&g.d_out, (size_t)C * g.af_size * sizeof(int16_t)));
     CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
     CK(cudaMemcpyAsync(g.d_tone, tone.data(), tone.size() * sizeof(float2), cudaMemcpyHostToDevice, rx->stream));
+    CK(cudaMemcpyAsync(g.d_pinc, pinc.data(), C * sizeof(float2), cudaMemcpyHostToDevice, rx->stream));
     CK(cudaMemcpyAsync(g.d_sign, sign.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
     CK(cudaMemcpyAsync(g.d_scale, scale.data(), C * sizeof(float), cudaMemcpyHostToDevice, rx->stream));
     CK(cudaMemsetAsync(g.d_maxbits, 0, C * sizeof(unsigned), rx->stream));
@@ -400,10 +419,24 @@ int commit_group_impl(cwsl_rx* rx, Group& g) {
     CK(cudaMemcpyAsync(g.d_chan, items.data(), items.size() * sizeof(cwsl::ChanItem), cudaMemcpyHostToDevice, rx->stream));
     CK(cudaStreamSynchronize(rx->stream));  // host vectors go out of scope
 
-    // phase tables: one per distinct (Fs, demodFreq, sideband, length), shared process-wide. New tables are built
-    // into local pointers and PUBLISHED to the cache only when they are complete: a failed build leaves nothing
-    // half-made behind, and nobody can ever pick up a table that is allocated but not yet filled.
+    // keys of the channels' phase recurrences (tables and anchors are built when a launch first needs them)
     const uint32_t length = (uint32_t)((g.af_size + 3) / 4 * 4 + 4);
+    g.phase_keys.clear();
+    for (uint32_t c = 0; c < C; ++c) g.phase_keys.push_back(PhaseKey{rx->device, rx->fs, g.ch[c].demod_freq, g.ch[c].usb, length});
+    g.have_phase_tables = false;
+    g.committed = true;
+    return CWSL_OK;
+}
+
+// Full phase tables P_c[k] = phase_inc_c^k (8 bytes per audio sample and channel), needed by the EXACT kernel and by
+// direct FAST launches; the STFT mode gets by with the anchors (ensure_stft) and never calls this. One table per
+// distinct (Fs, demodFreq, sideband, length), shared process-wide. New tables are built into local pointers and
+// PUBLISHED to the cache only when they are complete: a failed build leaves nothing half-made behind, and nobody can
+// ever pick up a table that is allocated but not yet filled.
+int ensure_phase_tables(cwsl_rx* rx, Group& g) {
+    if (g.have_phase_tables) return CWSL_OK;
+    const uint32_t C = (uint32_t)g.ch.size();
+    if (!commit_nosync()) CK(cudaDeviceSynchronize());  // one-time allocations on a quiet device, see commit_group()
     std::vector<const float2*> ptrs(C);
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -413,8 +446,9 @@ int commit_group_impl(cwsl_rx* rx, Group& g) {
         auto drop_fresh = [&] {
             for (auto& kv : fresh) cudaFree(kv.second);
         };
+        const uint32_t length = C ? g.phase_keys[0].length : 0;
         for (uint32_t c = 0; c < C; ++c) {
-            const PhaseKey k{rx->device, rx->fs, g.ch[c].demod_freq, g.ch[c].usb, length};
+            const PhaseKey& k = g.phase_keys[c];
             if (g_phase_cache.count(k) || fresh.count(k)) continue;
             float2* tab = nullptr;
             const cudaError_t err = cudaMalloc(&tab, (size_t)length * sizeof(float2));
@@ -445,15 +479,45 @@ int commit_group_impl(cwsl_rx* rx, Group& g) {
         }
         for (auto& kv : fresh) g_phase_cache[kv.first].table = kv.second;  // publish
         for (uint32_t c = 0; c < C; ++c) {
-            const PhaseKey k{rx->device, rx->fs, g.ch[c].demod_freq, g.ch[c].usb, length};
-            PhaseEntry& e = g_phase_cache[k];
+            PhaseEntry& e = g_phase_cache[g.phase_keys[c]];
             ++e.refs;
-            g.phase_keys.push_back(k);
             ptrs[c] = e.table;
         }
+        g.have_phase_tables = true;
     }
-    CK(cudaMemcpy((void*)g.d_phase, ptrs.data(), C * sizeof(float2*), cudaMemcpyHostToDevice));
-    g.committed = true;
+    CK(cudaMemcpyAsync((void*)g.d_phase, ptrs.data(), C * sizeof(float2*), cudaMemcpyHostToDevice, rx->stream));
+    CK(cudaStreamSynchronize(rx->stream));  // (ptrs goes out of scope)
+    return CWSL_OK;
+}
+
+void release_fast_scratch(cwsl_rx* rx) {
+    if (!rx->fast_scratch) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_fast_scratch.find({rx->device, rx->fast_scratch_stream});
+    if (it != g_fast_scratch.end() && --it->second.refs <= 0) {
+        cudaFree(it->second.p);
+        g_fast_scratch.erase(it);
+    }
+    rx->fast_scratch = nullptr;
+    rx->fast_scratch_stream = nullptr;
+}
+
+int ensure_fast_scratch(cwsl_rx* rx) {
+    if (rx->fast_scratch && rx->fast_scratch_stream == rx->stream) return CWSL_OK;
+    release_fast_scratch(rx);
+    std::lock_guard<std::mutex> lk(g_mu);
+    ScratchEntry& e = g_fast_scratch[{rx->device, rx->stream}];
+    if (!e.p) {
+        cudaError_t err = commit_nosync() ? cudaSuccess : cudaDeviceSynchronize();
+        if (err == cudaSuccess) err = cudaMalloc(&e.p, cwsl::fast_scratch_bytes(rx->device));
+        if (err != cudaSuccess) {
+            g_fast_scratch.erase({rx->device, rx->stream});
+            return fail(err == cudaErrorMemoryAllocation ? CWSL_ERR_NOMEM : CWSL_ERR_CUDA, "guard scratch: %s", cudaGetErrorString(err));
+        }
+    }
+    ++e.refs;
+    rx->fast_scratch = e.p;
+    rx->fast_scratch_stream = rx->stream;
     return CWSL_OK;
 }
 
@@ -469,7 +533,7 @@ int ensure_stft(cwsl_rx* rx, Group& g) {
             float2* tab = nullptr;
             cudaError_t err = commit_nosync() ? cudaSuccess : cudaDeviceSynchronize();
             if (err == cudaSuccess) err = cudaMalloc(&tab, (size_t)n_anchor * C * sizeof(float2));
-            if (err == cudaSuccess) err = cwsl::launch_phase_anchors(g.d_phase, tab, C, n_anchor, cwsl::kChanAnchorHops, rx->stream);
+            if (err == cudaSuccess) err = cwsl::launch_phase_anchors(g.d_pinc, tab, C, n_anchor, cwsl::kChanAnchorHops, rx->stream);
             if (err == cudaSuccess) err = cudaStreamSynchronize(rx->stream);
             if (err != cudaSuccess) {
                 cudaFree(tab);
@@ -598,7 +662,11 @@ int process_group(cwsl_rx* rx, Group& g, bool final) {
     const bool stft = g.mode == CWSL_MODE_STFT && p.n_channels >= stft_min_channels() && p.ring_blocks >= 64;
     // (IQ buffers shorter than two windows stay with the direct kernel)
     if (stft) {
-        const int rc = ensure_stft(rx, g);
+        int rc = ensure_stft(rx, g);
+        if (rc == CWSL_OK && rx->guard_db > 0) rc = ensure_fast_scratch(rx);
+        if (rc != CWSL_OK) return rc;
+    } else {  // EXACT and direct FAST launches read the full phase tables
+        const int rc = ensure_phase_tables(rx, g);
         if (rc != CWSL_OK) return rc;
     }
     // the post stream may still be normalising / copying the previous slot out of the buffers this launch rewrites
@@ -668,6 +736,10 @@ int process_group(cwsl_rx* rx, Group& g, bool final) {
             ind.n_items = g.d_n_items;
             ind.sel = g.d_sel;
             ind.sel_stride = p.n_channels;
+            ind.anchors = g.d_anchors;  // phases replayed from the exact checkpoints: no full tables in STFT mode
+            ind.anchor_stride = p.n_channels;
+            ind.pinc = g.d_pinc;
+            ind.scratch = rx->fast_scratch;
             CK(cwsl::launch_demod_fast(p, g.tiles, ind, rx->stream));
         }
     } else {
@@ -911,6 +983,7 @@ void cwsl_rx_destroy(cwsl_rx_t* rx) {
     if (rx->stream) cudaStreamSynchronize(rx->stream);
     if (rx->copy_stream) cudaStreamSynchronize(rx->copy_stream);
     for (Group& g : rx->groups) free_group_device(g);
+    release_fast_scratch(rx);
     cudaFree(rx->d_ring);
     for (auto& ev : rx->ev_demod)
         for (cudaEvent_t e : {ev.e0, ev.e_pre, ev.e_main, ev.e1})
@@ -941,6 +1014,7 @@ int cwsl_rx_set_stream(cwsl_rx_t* rx, void* cuda_stream) {
     CK(cudaStreamSynchronize(rx->stream));
     CK(cudaStreamSynchronize(rx->copy_stream));
     rx->d2h_pending = false;
+    release_fast_scratch(rx);
     if (rx->own_stream && rx->stream) cudaStreamDestroy(rx->stream);
     rx->stream = static_cast<cudaStream_t>(cuda_stream);
     rx->own_stream = false;
@@ -989,6 +1063,8 @@ int rebuild_group(cwsl_rx* rx, Group& g, std::vector<ChannelHost> channels) {
     g.have_anchor_ref = false;
     g.d_tone = nullptr;
     g.d_phase = nullptr;
+    g.d_pinc = nullptr;
+    g.have_phase_tables = false;
     g.d_sign = g.d_scale = g.d_factor = g.d_maxval = g.d_audio = g.d_seg_scale = nullptr;
     g.d_maxbits = g.d_seg_max = g.d_seg_energy = g.d_n_items = nullptr;
     g.d_sel = nullptr;

@@ -286,15 +286,52 @@ __global__ void __launch_bounds__(NT, CTAS)
             tma_bulk_g2s(smem_u32(xs + (size_t)t * Cfg::kRowStride), p.iq_ring + (size_t)row * BS, Cfg::kRowBytes,
                          bar_a);
         }
+        // Phase-table residency (STFT guard): replay this tile's phases from the anchors into the CTA's scratch slice.
+        // (channel, anchor interval) tasks of <= 128 sequential steps each, <= 5 intervals per tile; the previous
+        // tile's readers are past the __syncthreads that ends every channel.
+        const float2* scr = nullptr;
+        if constexpr (IND) {
+            if (ind.anchors) {
+                float2* scr_w = ind.scratch + (size_t)blockIdx.x * G * Cfg::kTile;
+                const int64_t k_lo = kt0 > 0 ? kt0 : 0, k_hi = min(kt0 + (int64_t)Cfg::kTile, (int64_t)p.b1);
+                if (k_hi > k_lo) {
+                    const uint32_t a_first = (uint32_t)(k_lo / kChanAnchorHops);
+                    const uint32_t n_int = (uint32_t)((k_hi - 1) / kChanAnchorHops) - a_first + 1u;
+                    for (uint32_t task = t; task < nch * n_int; task += NT) {
+                        const uint32_t ci = task / n_int, ai = a_first + task % n_int;
+                        const uint32_t c = cidx_s[ci] & kIdxMask;
+                        float2 P = __ldg(ind.anchors + (size_t)ai * ind.anchor_stride + c);
+                        const float2 inc = __ldg(ind.pinc + c);
+                        int64_t k = (int64_t)ai * kChanAnchorHops;
+                        const int64_t k_end = min(k + (int64_t)kChanAnchorHops, k_hi);
+                        float2* dst = scr_w + (size_t)ci * Cfg::kTile - kt0;
+                        for (; k < k_end; ++k) {
+                            if (k >= k_lo) dst[k] = P;
+                            const float x = __fmul_rn(P.x, inc.x), y = __fmul_rn(P.y, inc.y);  // phase_table_kernel's ops
+                            const float z = __fmul_rn(P.x, inc.y), w = __fmul_rn(P.y, inc.x);
+                            P = make_float2(__fsub_rn(x, y), __fadd_rn(z, w));
+                        }
+                    }
+                }
+                __syncthreads();
+                scr = scr_w - kt0;  // scr[ci * kTile + k]
+            }
+        }
         // phase values of my R blocks for the first channel (later channels are prefetched one ahead:
         // the tables live in HBM, ~1 us away at 2 warps per scheduler)
         float4 Pnext[R / 2];
 #pragma unroll
         for (int i = 0; i < R / 2; ++i) Pnext[i] = make_float4(1.f, 0.f, 1.f, 0.f);
         if (row_valid) {
-            const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[0] & kIdxMask] + kbase);
+            if (IND && scr) {
+                const float4* pp = reinterpret_cast<const float4*>(scr + kbase);
 #pragma unroll
-            for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
+                for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldcg(pp + i);  // (written by this CTA: not the read-only path)
+            } else {
+                const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[0] & kIdxMask] + kbase);
+#pragma unroll
+                for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
+            }
         }
         mbar_wait(bar_a, n_wait & 1u);
         ++n_wait;
@@ -328,9 +365,15 @@ __global__ void __launch_bounds__(NT, CTAS)
 #pragma unroll
                 for (int i = 0; i < R / 2; ++i) Pcur[i] = Pnext[i];
                 if (ci + 1 < nch) {
-                    const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[ci + 1] & kIdxMask] + kbase);
+                    if (IND && scr) {
+                        const float4* pp = reinterpret_cast<const float4*>(scr + (size_t)(ci + 1) * Cfg::kTile + kbase);
 #pragma unroll
-                    for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
+                        for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldcg(pp + i);
+                    } else {
+                        const float4* pp = reinterpret_cast<const float4*>(p.phase[cidx_s[ci + 1] & kIdxMask] + kbase);
+#pragma unroll
+                        for (int i = 0; i < R / 2; ++i) Pnext[i] = __ldg(pp + i);
+                    }
                 }
 #pragma unroll(kFastRUnroll)
                 for (int r = 0; r < R; ++r) {
@@ -747,6 +790,12 @@ cudaError_t launch_demod_exact(const DemodLaunch& p, cudaStream_t s) {
     }
 }
 
+size_t fast_scratch_bytes(int device) {  // indirect launches: sms x 2 CTAs, each kFastGMax channels x kFastTile blocks
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+    return (size_t)sms * 2 * kFastGMax * kFastTile * sizeof(float2);
+}
+
 cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, const FastIndirect& ind, cudaStream_t s) {
     if (p.b1 <= p.b0 || p.n_channels == 0) return cudaSuccess;
     if (tiles_per_seg == 0) return cudaErrorInvalidValue;
@@ -861,20 +910,28 @@ cudaError_t launch_clear_u32(unsigned* p, uint32_t n, unsigned long long* counte
     return cudaGetLastError();
 }
 
-// P_c[spacing * a] of every channel's exact phase table, [anchor][channel] (coalesced for the STFT consumers)
-__global__ void phase_anchor_kernel(const float2* const* __restrict__ phase, float2* __restrict__ anchors, uint32_t n_channels,
-                                    uint64_t total, uint32_t spacing) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const uint64_t a = i / n_channels;
-    const uint32_t c = (uint32_t)(i - a * n_channels);
-    anchors[i] = __ldg(phase[c] + a * spacing);
+// P_c[spacing * a] of every channel's phase recurrence, [anchor][channel] (coalesced for the STFT consumers): the exact
+// checkpoints from which the STFT mode's kernels replay what they need, instead of 8 bytes per audio sample of table.
+__global__ void phase_anchor_kernel(const float2* __restrict__ inc, float2* __restrict__ anchors, uint32_t n_channels,
+                                    uint32_t n_anchor, uint32_t spacing) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_channels) return;
+    const float ir = inc[c].x, ii = inc[c].y;
+    float pr = 1.0f, pi = 0.0f;
+    for (uint32_t a = 0; a < n_anchor; ++a) {
+        anchors[(size_t)a * n_channels + c] = make_float2(pr, pi);
+        for (uint32_t j = 0; j < spacing; ++j) {  // the same operations, in the same order, as phase_table_kernel
+            const float x = __fmul_rn(pr, ir), y = __fmul_rn(pi, ii);
+            const float z = __fmul_rn(pr, ii), w = __fmul_rn(pi, ir);
+            pr = __fsub_rn(x, y);
+            pi = __fadd_rn(z, w);
+        }
+    }
 }
-cudaError_t launch_phase_anchors(const float2* const* phase, float2* anchors, uint32_t n_channels, uint32_t n_anchor,
+cudaError_t launch_phase_anchors(const float2* phase_inc, float2* anchors, uint32_t n_channels, uint32_t n_anchor,
                                  uint32_t spacing, cudaStream_t s) {
-    const uint64_t total = (uint64_t)n_channels * n_anchor;
-    if (total == 0) return cudaSuccess;
-    phase_anchor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(phase, anchors, n_channels, total, spacing);
+    if (n_channels == 0 || n_anchor == 0) return cudaSuccess;
+    phase_anchor_kernel<<<(n_channels + 31) / 32, 32, 0, s>>>(phase_inc, anchors, n_channels, n_anchor, spacing);
     return cudaGetLastError();
 }
 

@@ -65,7 +65,16 @@ struct FastIndirect {
     const unsigned* n_items = nullptr;  // device counter written by guard_select_kernel
     const uint32_t* sel = nullptr;      // [n_seg][sel_stride] channel indices, ascending per segment
     uint32_t sel_stride = 0;
+    // Phase-table residency: with anchors != nullptr the kernel never reads DemodLaunch::phase. Every CTA replays the
+    // reference's exact float recurrence (source/SSBD.hpp:174) from the anchors P_c[128 a] for the <= 32 channels and
+    // 512 blocks of the tile it is about to process, into its own slice of `scratch` -- the same bits as the full
+    // table, at 1/128 of its memory plus a fixed 39 MB of scratch per stream.
+    const float2* anchors = nullptr;    // [anchor][anchor_stride]
+    uint32_t anchor_stride = 0;
+    const float2* pinc = nullptr;       // [n_channels] the reference's float phase_inc
+    float2* scratch = nullptr;          // [grid][kFastGMax][kFastTile], see fast_scratch_bytes()
 };
+size_t fast_scratch_bytes(int device);  // scratch of one indirect FAST launch on this device
 
 // Extra inputs of the STFT channelizer kernel (cwsl_chan.cu); tables from cwsl_tables.hpp chan_*.
 constexpr int kChanTaps = 8;                   // stencil bins per channel of the host-side description (cwsl_stft_channel)
@@ -137,8 +146,9 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, cons
 // STFT channelizer (<= kChanMaxItems work items per launch; DemodLaunch names the whole slot group); p.b0 must be a
 // multiple of 32
 cudaError_t launch_demod_chan(const DemodLaunch& p, const ChanLaunch& c, cudaStream_t s);
-// P_c[spacing * a] gathered from the full phase tables into [n_anchor][n_channels]
-cudaError_t launch_phase_anchors(const float2* const* phase, float2* anchors, uint32_t n_channels, uint32_t n_anchor,
+// P_c[spacing * a], a < n_anchor, by the reference's unfused float recurrence (one thread per channel, sequential by
+// construction) into [n_anchor][n_channels]: the exact checkpoints of every channel's phase table
+cudaError_t launch_phase_anchors(const float2* phase_inc, float2* anchors, uint32_t n_channels, uint32_t n_anchor,
                                  uint32_t spacing, cudaStream_t s);
 // Guard: per-segment band power -> seg_scale (before the channelizer), selection + max merge (after it)
 cudaError_t launch_guard_band_power(const DemodLaunch& p, const GuardLaunch& g, cudaStream_t s);
