@@ -171,7 +171,12 @@ constexpr int kThreads = kFftThreads + kIntThreads;
 // interpolation warps (4 x 9 weights + a 12-bin window + 32 outputs in flight per thread) take them (setmaxnreg).
 // 512 x 120 leaves 4 K registers per SM for a CTA of the (HBM-bound) quantise kernel of the previous receiver, which
 // then runs underneath this (shared-memory-bound) kernel instead of after it.
-constexpr int kLaunchRegs = 120, kFftRegs = 96, kIntRegs = 144;
+#ifndef CWSL_CHAN_LAUNCH_REGS  // (A/B builds: -DCWSL_CHAN_LAUNCH_REGS= -DCWSL_CHAN_FFT_REGS= -DCWSL_CHAN_INT_REGS=)
+#define CWSL_CHAN_LAUNCH_REGS 120
+#define CWSL_CHAN_FFT_REGS 88
+#define CWSL_CHAN_INT_REGS 152
+#endif
+constexpr int kLaunchRegs = CWSL_CHAN_LAUNCH_REGS, kFftRegs = CWSL_CHAN_FFT_REGS, kIntRegs = CWSL_CHAN_INT_REGS;
 static_assert(kFftThreads * kFftRegs + kIntThreads * kIntRegs <= kThreads * kLaunchRegs, "register budget");
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
