@@ -411,7 +411,10 @@ def run_b200(a):
             return dict(
                 bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak,
                 traffic=tj.get("dram_bytes_per_launch"),
-                kernel="demod_chan_kernel<16,4> (STFT channelizer: FFT warps + interpolation warps per SM, persistent)",
+                kernel="demod_chan_kernel<16> (STFT channelizer: 8 FFT warps + 8 interpolation warps per SM, persistent)",
+                limiter="no unit saturated (ncu, profiles/r2_demod_chan_final_ncu_full.csv): FMA pipe 54 %, shared-memory "
+                        "wavefronts 57 %, issue slots 44 % with 16 resident warps per SM (registers + 215 KB of shared "
+                        "memory cap the occupancy); the HBM fraction is what the contract asks for, the kernel is not HBM-bound",
                 launch_ms=launch_ms, launches_timed=launches, value=val, ms_per_step=ms_per_step, steps=t["steps"],
                 guard_ms_per_launch=(t["guard_pre_ms"] + t["guard_post_ms"]) / launches,
                 kernel_share_of_step=iso["main_kernel_ms"] / (iso["demod_ms"] + iso["quantise_and_clear_ms"]),
@@ -429,9 +432,8 @@ def run_b200(a):
                     frac_of_lsu_peak=(wf / cyc if wf else None), frac_of_lsu_peak_isolated=(wf / cyc_iso if wf else None),
                     ncu_pct_of_peak=tj.get("shared_wavefront_pct"), ncu_fma_pipe_pct=tj.get("fma_pipe_pct"),
                     ncu_issue_active_pct=tj.get("issue_active_pct"),
-                    note="the kernel's real limiter: l1tex shared-memory wavefronts (ncu count of one launch, committed "
-                         "under profiles/) / (SMs x SM cycles of launch_ms at the sampled clock), peak = 1 wavefront per "
-                         "SM per cycle"),
+                    note="l1tex shared-memory wavefronts (ncu count of one launch, committed under profiles/) / (SMs x SM "
+                         "cycles of launch_ms at the sampled clock), peak = 1 wavefront per SM per cycle"),
                 direct_form_equivalent=dict(
                     tflops=FLOP_PER_CH_SAMPLE * val * 1e6 / 1e12, fp32_peak_tflops=peak_tf,
                     note="134 flop per channel-sample (SURVEY.md 8d, direct form) x throughput, for comparison with the "

@@ -63,8 +63,9 @@ inline Decoder parseDecoderLine(const std::string& rawLine, double freqCalGlobal
     return Decoder(freq, calibrated, mode, smnum, decoder_freqcal, callsign);
 }
 
-// Minimal INI reader for the keys above ([section] headers, key=value, '#'/';' comments), the
-// format boost::program_options::parse_config_file accepts (source/CWSL_DIGI.cpp:607-611).
+// Minimal INI reader for the keys above ([section] headers, key=value, '#' starts a comment anywhere in a line), the
+// format boost::program_options::parse_config_file accepts (source/CWSL_DIGI.cpp:607-611). ';' is NOT a comment
+// character there, so it is not one here either.
 inline FrontEndConfig loadFrontEndConfig(std::istream& in) {
     FrontEndConfig cfg;
     std::vector<std::string> decoderLines;
@@ -76,7 +77,7 @@ inline FrontEndConfig loadFrontEndConfig(std::istream& in) {
         return s.substr(b, s.find_last_not_of(ws) - b + 1);
     };
     while (std::getline(in, line)) {
-        const auto hash = line.find_first_of("#;");
+        const auto hash = line.find('#');
         if (hash != std::string::npos) line = line.substr(0, hash);
         line = trim(line);
         if (line.empty()) continue;
