@@ -146,6 +146,7 @@ struct Group {
     uint64_t processed = 0;    // slot-relative blocks already demodulated
     uint64_t iq_blocks = 0;    // IQ blocks pushed since the slot edge
     size_t last_write_index = 0;
+    size_t out_dirty = 0;      // columns [0, out_dirty) of d_out may be non-zero; the quantise pass rewrites only those
     bool have_result = false;
     bool committed = false;
 };
@@ -382,6 +383,7 @@ int commit_group_impl(cwsl_rx* rx, Group& g) {
     CK(cudaMalloc(&g.d_maxval, C * sizeof(float)));
     CK(cudaMalloc(&g.d_audio, (size_t)C * g.af_stride * sizeof(float)));
     CK(cudaMalloc(&g.d_out, (size_t)C * g.af_size * sizeof(int16_t)));
+    g.out_dirty = g.af_size;  // nothing is known about the fresh buffer: the first slot writes every column
     CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
     CK(cudaMemcpyAsync(g.d_tone, tone.data(), tone.size() * sizeof(float2), cudaMemcpyHostToDevice, rx->stream));
     CK(cudaMemcpyAsync(g.d_pinc, pinc.data(), C * sizeof(float2), cudaMemcpyHostToDevice, rx->stream));
@@ -1255,6 +1257,7 @@ int end_slot_work(cwsl_rx* rx, Group* g, int16_t* out_i16) {
     q.n_channels = C;
     q.write_index = (uint32_t)g->processed;
     q.af_size = (uint32_t)g->af_size;
+    q.cover = (uint32_t)std::max<size_t>(g->out_dirty, (size_t)g->processed);
     q.maxbits = g->d_maxbits;
     q.scale = g->d_scale;
     q.out = g->d_out;
@@ -1274,6 +1277,7 @@ int end_slot_work(cwsl_rx* rx, Group* g, int16_t* out_i16) {
         CK(cudaEventRecord(e0, rx->copy_stream));
     }
     CK(cwsl::launch_quantise(q, rx->copy_stream));
+    g->out_dirty = (size_t)g->processed;
     // next slot starts from max|x| = 0; the guard's counters roll over to "last finished slot"
     CK(cwsl::launch_clear_u32(g->d_maxbits, C, g->d_counters, rx->copy_stream));
     if (rx->timing) {

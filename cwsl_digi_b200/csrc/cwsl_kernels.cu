@@ -890,7 +890,9 @@ __global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
 cudaError_t launch_quantise(const QuantLaunch& p, cudaStream_t s) {
     if (p.n_channels == 0 || p.af_size == 0) return cudaSuccess;
     const uint32_t per_cta = kQuantThreads * 8u * (uint32_t)kQuantVec;
-    dim3 grid((p.af_size + per_cta - 1) / per_cta, p.n_channels);
+    // the zero tail behind `cover` is already zero in `out` (previous slots never wrote there): not written again
+    const uint32_t cover = std::min(p.af_size, std::max(p.cover, p.write_index));
+    dim3 grid((cover + per_cta - 1) / per_cta, p.n_channels);
     quantise_kernel<kQuantVec, kQuantRegs><<<grid, kQuantThreads, 0, s>>>(p);
     return cudaGetLastError();
 }

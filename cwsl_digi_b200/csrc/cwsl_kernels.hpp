@@ -34,6 +34,7 @@ struct QuantLaunch {
     uint32_t n_channels = 0;
     uint32_t write_index = 0;  // samples demodulated this slot
     uint32_t af_size = 0;      // (period+5 s)*12000
+    uint32_t cover = 0;        // columns [0, cover) of `out` are written (>= write_index: the rest is known to be zero)
     const unsigned* maxbits = nullptr;
     const float* scale = nullptr;  // [n_channels]
     int16_t* out = nullptr;        // [n_channels][af_size]

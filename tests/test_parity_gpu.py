@@ -205,6 +205,42 @@ def test_consecutive_slots_and_two_groups(gpu, ref):
         assert wi == o["write_index"] and np.array_equal(out[0], o["i16"])
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_slots_of_different_length_keep_the_zero_tail(gpu, ref, mode):
+    """Slots of 30, 12, 20 and 6 IQ blocks on one handle, taken to a device buffer AND to the host: the library rewrites
+    only the columns a previous slot may have left non-zero (quantise pass) and copies only those (hand-off buffer), so
+    a short slot after a long one is where a stale tail would show. Every int16 vector must equal the oracle's over the
+    whole (period + 5 s) buffer (source/Instance.cpp:149, :294-338)."""
+    cw = gpu
+    fs, iq_len = 192000, 2048
+    chans = [(-26000, 0.9), (31000, 0.5)]
+    lengths = [30, 12, 20, 6]
+    iq = synth.receiver_iq(sum(lengths) * iq_len, fs, [c[0] for c in chans], receiver=21, tones_per_channel=2)
+    afs = af_size(15)
+    host = cw.HostBuffer(len(chans), afs)
+    try:
+        with cw.Receiver(0, fs, iq_len, ring_seconds=0.5, mode=_mode(cw, mode)) as rx:
+            g = rx.add_group(15.0)
+            for f, sc in chans:
+                rx.add_channel(g, f, sc)
+            pos = 0
+            for n in lengths:
+                span = iq[pos * iq_len * 2:(pos + n) * iq_len * 2]
+                pos += n
+                rx.push_iq(span)
+                wi = rx.end_slot(g, host.ptr)
+                rx.wait_output()
+                got = host.array.copy()
+                for c, (f, sc) in enumerate(chans):
+                    o = ref.slot(fs, f, span, iq_len, sc, afs)
+                    assert wi == o["write_index"]
+                    d = np.abs(got[c].astype(np.int32) - o["i16"].astype(np.int32))
+                    assert d.max() <= (0 if mode == "exact" else FAST_MAX_LSB), (n, c, int(d.max()))
+                    assert not got[c][wi:].any(), f"stale samples behind write_index after a {n}-block slot"
+    finally:
+        host.free()
+
+
 def test_mode_switch_between_slots_and_stft_slot_purity(gpu, ref):
     """One receiver, five consecutive slots with the arithmetic mode changed at the slot edges
     (STFT, STFT, FAST, EXACT, STFT): every slot starts from fresh SSBD state (Instance.cpp:251; for STFT: zero
