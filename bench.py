@@ -476,9 +476,19 @@ def run_b200(a):
     # ---- device-resident arm, --mode ---------------------------------------------------------------
     main_t = timed_resident(a.steps, max(3, a.warmup), True)
     clk = main_t["clocks"]
+    per_rx = a.channels * afs * (4 + 2)          # float audio scratch + int16 hand-off buffer of one receiver
+    n_anchor = afs // 128 + 1                      # cwsl_kernels.hpp kChanAnchorHops
     footprint = dict(device_bytes_per_rank=int(free0 - torch.cuda.mem_get_info()[0]), receivers=len(rxs),
-                     note="cudaMemGetInfo delta over receiver creation + first launches: phase tables (shared by the "
-                          "receivers), float audio scratch and int16 hand-off buffers of every receiver, STFT tables")
+                     audio_and_handoff_bytes_per_receiver=int(per_rx),
+                     phase_state_bytes=(dict(kind="anchors of the exact phase recurrence every 128 hops, shared by all "
+                                                  "receivers with the same channel set (STFT mode keeps no full tables)",
+                                             bytes=int(n_anchor * a.channels * 8))
+                                        if a.mode == "stft" and a.channels >= 64 else
+                                        dict(kind="full phase tables, 8 B per audio sample and distinct channel, shared by "
+                                                  "all receivers", bytes=int((afs + 4) * a.channels * 8))),
+                     note="cudaMemGetInfo delta over receiver creation + the timed steps of --mode (before the other "
+                          "modes run): float audio scratch and int16 hand-off buffer of every receiver, phase state, "
+                          "per-channel constants, STFT tables and guard scratch")
     iso_main = isolated() if rank == 0 else None
     barrier()
     ms_step = main_t["ms_step"]
