@@ -22,6 +22,21 @@ for mode in (cw.MODE_FAST, cw.MODE_EXACT, cw.MODE_STFT):
             rx.push_iq(iq[b * IQ_LEN * 2:(b + 7) * IQ_LEN * 2])
         out, wi = rx.end_slot_numpy(g)
         print("mode", mode, "wi", wi, "checksum", int(out.astype(np.int64).sum()))
+# the STFT guard's redo path: one carrier ~80 dB over the noise, so the quiet channels' segments are recomputed by the
+# indirect FAST launch (work lists built on the device, phases replayed from the anchors into the per-stream scratch)
+hdr = iq.copy()
+t = np.arange(hdr.size // 2, dtype=np.float64)
+ph = 2 * np.pi * ((freqs[5] + 1500.0) * t % FS) / FS
+hdr[0::2] = hdr[0::2] * 0.01 + (3.0e4 * np.cos(ph)).astype(np.float32)
+hdr[1::2] = hdr[1::2] * 0.01 + (3.0e4 * np.sin(ph)).astype(np.float32)
+with cw.Receiver(0, FS, IQ_LEN, ring_seconds=0.3, mode=cw.MODE_STFT) as rx:
+    g = rx.add_group(15.0)
+    for f in freqs:
+        rx.add_channel(g, f, 0.9)
+    for b in range(0, 70, 7):
+        rx.push_iq(hdr[b * IQ_LEN * 2:(b + 7) * IQ_LEN * 2])
+    out, wi = rx.end_slot_numpy(g)
+    print("stft guard redo: wi", wi, "checksum", int(out.astype(np.int64).sum()), "guard", rx.guard_stats(g))
 # the channelizer's other geometries (two / four hops per FFT warp): 96 and 48 kHz receivers
 for fs, il in ((96000, 1024), (48000, 512)):
     fr = [int(f) for f in np.linspace(-fs // 2, fs // 2 - 6000, 20)]
