@@ -347,10 +347,14 @@ int commit_device_tables(cwsl_rx* rx) {
         const std::vector<float> w = cwsl::chan_window(rx->geo, cwsl::kChanKernelWidth);
         const std::vector<std::complex<float>> tw = cwsl::chan_twiddles(rx->geo);
         ChanDeviceTables t;
-        CK(cudaMalloc(&t.window, w.size() * sizeof(float)));
-        CK(cudaMalloc(&t.twiddle, tw.size() * sizeof(float2)));
-        CK(cudaMemcpy(t.window, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(t.twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        cudaError_t err = cudaMalloc(&t.window, w.size() * sizeof(float));
+        if (err == cudaSuccess) err = cudaMalloc(&t.twiddle, tw.size() * sizeof(float2));
+        if (err == cudaSuccess) err = cudaMemcpy(t.window, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (err == cudaSuccess) err = cudaMemcpy(t.twiddle, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice);
+        if (err != cudaSuccess) {  // published only when complete
+            cudaFree(t.window), cudaFree(t.twiddle);
+            return fail(err == cudaErrorMemoryAllocation ? CWSL_ERR_NOMEM : CWSL_ERR_CUDA, "STFT tables: %s", cudaGetErrorString(err));
+        }
         g_chan_tables[key] = t;
     }
     rx->chan_tables = g_chan_tables[key];
@@ -550,19 +554,27 @@ int ensure_stft(cwsl_rx* rx, Group& g) {
         g.have_anchor_ref = true;
         g.d_anchors = e.table;
     }
-    if (!g.d_seg_scale) {
+    if (g.max_segs == 0) {  // (set last: a failed attempt is rolled back and repeated by the next launch)
         const uint32_t W = cwsl::fast_seg_blocks(g.tiles);
         const uint32_t segs = (uint32_t)(g.af_size / W + 2);
         if (!commit_nosync()) CK(cudaDeviceSynchronize());
-        CK(cudaMalloc(&g.d_seg_scale, segs * sizeof(float)));
-        CK(cudaMalloc(&g.d_seg_max, (size_t)segs * C * sizeof(unsigned)));
-        CK(cudaMalloc(&g.d_seg_energy, (size_t)segs * C * sizeof(unsigned)));
-        CK(cudaMalloc(&g.d_sel, (size_t)segs * C * sizeof(uint32_t)));
-        CK(cudaMalloc(&g.d_items, (size_t)segs * ((C + 31) / 32) * sizeof(cwsl::GuardItem)));
-        CK(cudaMalloc(&g.d_n_items, sizeof(unsigned)));
-        CK(cudaMemsetAsync(g.d_seg_max, 0, (size_t)segs * C * sizeof(unsigned), rx->stream));
-        CK(cudaMemsetAsync(g.d_seg_energy, 0, (size_t)segs * C * sizeof(unsigned), rx->stream));
-        CK(cudaMemsetAsync(g.d_n_items, 0, sizeof(unsigned), rx->stream));
+        cudaError_t err = cudaMalloc(&g.d_seg_scale, segs * sizeof(float));
+        if (err == cudaSuccess) err = cudaMalloc(&g.d_seg_max, (size_t)segs * C * sizeof(unsigned));
+        if (err == cudaSuccess) err = cudaMalloc(&g.d_seg_energy, (size_t)segs * C * sizeof(unsigned));
+        if (err == cudaSuccess) err = cudaMalloc(&g.d_sel, (size_t)segs * C * sizeof(uint32_t));
+        if (err == cudaSuccess) err = cudaMalloc(&g.d_items, (size_t)segs * ((C + 31) / 32) * sizeof(cwsl::GuardItem));
+        if (err == cudaSuccess) err = cudaMalloc(&g.d_n_items, sizeof(unsigned));
+        if (err == cudaSuccess) err = cudaMemsetAsync(g.d_seg_max, 0, (size_t)segs * C * sizeof(unsigned), rx->stream);
+        if (err == cudaSuccess) err = cudaMemsetAsync(g.d_seg_energy, 0, (size_t)segs * C * sizeof(unsigned), rx->stream);
+        if (err == cudaSuccess) err = cudaMemsetAsync(g.d_n_items, 0, sizeof(unsigned), rx->stream);
+        if (err != cudaSuccess) {
+            cudaFree(g.d_seg_scale), cudaFree(g.d_seg_max), cudaFree(g.d_seg_energy);
+            cudaFree(g.d_sel), cudaFree(g.d_items), cudaFree(g.d_n_items);
+            g.d_seg_scale = nullptr, g.d_seg_max = g.d_seg_energy = g.d_n_items = nullptr, g.d_sel = nullptr, g.d_items = nullptr;
+            cudaGetLastError();
+            return fail(err == cudaErrorMemoryAllocation ? CWSL_ERR_NOMEM : CWSL_ERR_CUDA, "STFT guard scratch: %s",
+                        cudaGetErrorString(err));
+        }
         g.max_segs = segs;
     }
     return CWSL_OK;
@@ -974,6 +986,10 @@ cwsl_rx_t* cwsl_rx_create(int device, uint32_t sample_rate, uint32_t iq_len, dou
         cudaEventCreateWithFlags(&rx->ev_out_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&rx->ev_d2h_done, cudaEventDisableTiming) != cudaSuccess) {
         fail(CWSL_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rx->stream) cudaStreamDestroy(rx->stream);  // whatever part of the set exists
+        if (rx->copy_stream) cudaStreamDestroy(rx->copy_stream);
+        if (rx->ev_out_ready) cudaEventDestroy(rx->ev_out_ready);
+        if (rx->ev_d2h_done) cudaEventDestroy(rx->ev_d2h_done);
         return nullptr;
     }
     return rx.release();
