@@ -57,8 +57,8 @@ FAST_TILE_OVERHEAD = 1536.0 / 1504.0
 EXACT_LANE_SLOTS_PER_CH_SAMPLE = 150.0
 METRIC, UNIT = "channel-Msamples/s (IQ in x decoders)", "ch-Msamples/s"
 NCU_COUNTERS = {   # ncu --set full captures committed under profiles/ (one launch each, 1024 ch x FT8 slot unless noted)
-    "fast": dict(file="profiles/r1_demod_fast_final_ncu_full.csv", sm__pipe_fma_cycles_active_pct=83.0, issue_active_pct=48.0),
-    "exact": dict(file="profiles/r1_demod_exact_tiled_ncu_full.csv", sm__pipe_fma_cycles_active_pct=77.0, issue_active_pct=64.0,
+    "fast": dict(file="profiles/r2_demod_fast_ncu_full.csv", sm__pipe_fma_cycles_active_pct=82.8, issue_active_pct=48.4),
+    "exact": dict(file="profiles/r2_demod_exact_tiled_ncu_full.csv", sm__pipe_fma_cycles_active_pct=77.8, issue_active_pct=64.0,
                   note="256-channel launch"),
 }
 
