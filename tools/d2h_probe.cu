@@ -83,6 +83,8 @@ int main() {
         gp[i] = timed([&] { cudaMemcpy2DAsync(hbig, hp, d, pitch, width, rows, cudaMemcpyDeviceToHost, st[0]); });
     }
     const double gp_dev = timed([&] { cudaMemcpy2DAsync(hbig, 483328, d, 483328, width, rows - 8, cudaMemcpyDeviceToHost, st[0]); });
+    // packed destination: rows land back to back on the host (dst pitch = row width), the source keeps its pitch
+    const double gpk = timed([&] { cudaMemcpy2DAsync(hbig, width, d, pitch, width, rows, cudaMemcpyDeviceToHost, st[0]); });
     int engines = 0;
     cudaDeviceGetAttribute(&engines, cudaDevAttrAsyncEngineCount, 0);
     std::printf("{\"what\": \"int16 hand-off of one receiver to pinned host memory, GB/s of the %zu demodulated bytes\", "
@@ -90,7 +92,7 @@ int main() {
                 "\"memcpy_2d_4streams\": %.2f, \"memcpy_2d_4receivers_in_flight\": %.2f, "
                 "\"kernel_zero_copy_148x256\": %.2f, \"kernel_zero_copy_296x256\": %.2f, \"kernel_zero_copy_1184x256\": %.2f, "
                 "\"memcpy_2d_host_pitch_480000\": %.2f, \"memcpy_2d_host_pitch_480256\": %.2f, \"memcpy_2d_host_pitch_483328\": %.2f, "
-                "\"memcpy_2d_host_pitch_524288\": %.2f, \"memcpy_2d_both_pitches_483328\": %.2f}\n",
-                rows * width, engines, g1d, g2d, g2d2, g2d4, g2dq, gk[0], gk[1], gk[2], gp[0], gp[1], gp[2], gp[3], gp_dev);
+                "\"memcpy_2d_host_pitch_524288\": %.2f, \"memcpy_2d_both_pitches_483328\": %.2f, \"memcpy_2d_packed_destination\": %.2f}\n",
+                rows * width, engines, g1d, g2d, g2d2, g2d4, g2dq, gk[0], gk[1], gk[2], gp[0], gp[1], gp[2], gp[3], gp_dev, gpk);
     return 0;
 }
