@@ -421,6 +421,12 @@ def run_b200(a):
                 share_note="serialised share (each receiver alone on the device, CUDA events): comparable with the ncu "
                            "launch list under profiles/. In the timed region the quantise pass of receiver r runs on the "
                            "post stream beside the channelizer of r+1, and launch_ms there includes waiting for its CTAs",
+                step_hbm=dict(
+                    bytes_per_receiver=int(stft_bytes + a.channels * (n_iq // 16) * (4 + 2)),
+                    achieved_gbs=(stft_bytes + a.channels * (n_iq // 16) * (4 + 2)) * len(rxs) / (ms_per_step * 1e-3) / 1e9,
+                    frac=(stft_bytes + a.channels * (n_iq // 16) * (4 + 2)) * len(rxs) / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                    note="whole step: channelizer bytes + the normalise/quantise pass (float audio read, int16 written) of "
+                         "every receiver of this rank / ms_per_step"),
                 launch_ms_isolated=iso["main_kernel_ms"],
                 achieved_isolated=stft_bytes / (iso["main_kernel_ms"] * 1e-3) / 1e9,
                 frac_isolated=stft_bytes / (iso["main_kernel_ms"] * 1e-3) / 1e9 / hbm_peak,
