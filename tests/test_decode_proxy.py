@@ -1,14 +1,16 @@
 """Executable stand-in for north_star's decode-set gate (see tests/decode_proxy.py for what it is and is not):
-FT8-shaped 8-FSK signals from +0 dB to -24 dB (in 2500 Hz) go through the reference chain (oracle) and through the GPU
-modes; a non-coherent demodulator -- Costas sync search, per-symbol tone energies, hard decisions, soft metrics -- must
-produce the same output from both int16 buffers. EXACT hands over identical buffers (checked elsewhere, bit for bit);
-this is the evidence for FAST and STFT, whose buffers differ from the reference's by <= 1 LSB in ~0.1 % of the samples.
+FT8-, FT4- and WSPR-shaped M-FSK signals from 0 dB down to below each mode's decoding threshold (in 2500 Hz) go through
+the reference chain (oracle) and through the GPU modes; a non-coherent demodulator -- sync search over time and frequency,
+per-symbol tone energies, hard decisions, soft metrics -- must produce the same output from both int16 buffers. EXACT
+hands over identical buffers (checked elsewhere, bit for bit); this is the evidence for FAST and STFT, whose buffers
+differ from the reference's by <= 1 LSB in ~0.1 % of the samples.
 
-Measured on B200: without a dominant carrier every sync position and all 632 hard decisions agree in FAST and STFT.
+Measured on B200: without a dominant carrier every sync position and every hard decision agrees in FAST and STFT, for
+all three waveforms (WSPR-shaped: a 120 s slot, 1.44 M steps of the drifting float NCO recurrence).
 With a carrier 70 dB (2500 Hz) over the noise elsewhere in the band, FAST -- and STFT, whose guard hands those channel
 segments to the FAST kernel -- differ from EXACT by the float32 rounding of that carrier's partial sums (~1e-7 of the
-band), and ONE decision of the -24 dB signal (3 dB under FT8's threshold, 42 of its 79 decisions are wrong anyway)
-flips at a tie of its two best tones; soft metrics still agree to 1e-3. That is the documented limit of the
+band), and ONE decision of the FT8-shaped -24 dB signal (3 dB under FT8's threshold, 42 of its 79 decisions are wrong
+anyway) flips at a tie of its two best tones; soft metrics still agree to 1e-3. That is the documented limit of the
 FAST-tolerance modes; EXACT has none."""
 import numpy as np
 import pytest
@@ -18,73 +20,91 @@ from cwsl_digi_b200 import synth
 from oracle.oracle import af_size
 
 FS, IQ_LEN = 192000, 2048
-NBLK = 15 * FS // IQ_LEN
-N = NBLK * IQ_LEN
 SIGMA = 300.0
-# (channel, SNR dB in 2500 Hz, audio frequency of tone 0 (multiple of 6.25 Hz), start time in the slot)
-PLAN = [(0, 0.0, 500.0, 0.50), (0, -10.0, 1000.0, 0.62), (0, -16.0, 1500.0, 0.74), (0, -20.0, 2000.0, 0.40),
-        (0, -24.0, 2400.0, 0.80), (1, -12.0, 800.0, 0.55), (1, -21.0, 1750.0, 0.66), (2, -18.0, 1200.0, 0.58)]
-DEMOD = [-26000, 31000, 88000]
 SOFT_TOL = 1e-3            # on soft metrics that are normalised to 1 per symbol
-FT8_THRESHOLD_DB = -21.0   # WSJT-X quotes -21 dB (2500 Hz) as FT8's decoding threshold
+# per waveform: slot period, decoding threshold WSJT-X quotes (dB in 2500 Hz), decoder channels (demod Hz),
+# signals (channel, SNR dB, tone-0 audio frequency as a multiple of the tone spacing, start time in the slot)
+CASES = {
+    "ft8": dict(wf=dp.FT8, period=15.0, threshold=-21.0, demod=[-26000, 31000, 88000],
+                plan=[(0, 0.0, 80, 0.50), (0, -10.0, 160, 0.62), (0, -16.0, 240, 0.74), (0, -20.0, 320, 0.40),
+                      (0, -24.0, 384, 0.80), (1, -12.0, 128, 0.55), (1, -21.0, 280, 0.66), (2, -18.0, 192, 0.58)]),
+    "ft4": dict(wf=dp.FT4, period=7.5, threshold=-17.5, demod=[-26000, 44000],
+                plan=[(0, 0.0, 30, 0.50), (0, -10.0, 60, 0.55), (0, -16.0, 90, 0.45), (0, -20.0, 115, 0.60),
+                      (1, -14.0, 48, 0.52), (1, -18.0, 100, 0.48)]),
+    "wspr": dict(wf=dp.WSPR, period=120.0, threshold=-31.0, demod=[-26000],
+                 plan=[(0, -10.0, 960, 1.0), (0, -24.0, 1000, 1.5), (0, -30.0, 1040, 2.0), (0, -33.0, 1080, 1.2)]),
+}
 
 
-def build_iq(strong_carrier=False):
+def build_iq(case, strong_carrier=False):
+    wf = case["wf"]
+    n = int(case["period"] * FS) // IQ_LEN * IQ_LEN
     rng = np.random.default_rng(20261017)
-    x = synth.gaussian_iq(N, receiver=31, sigma=SIGMA)
+    x = synth.gaussian_iq(n, receiver=31, sigma=SIGMA)
     z = x[:, 0] + 1j * x[:, 1]
+    del x
     sigs = []
-    for ch, snr, fa, t0 in PLAN:
-        sym = dp.make_symbols(rng)
-        z = z + dp.fsk_iq(N, FS, DEMOD[ch] + fa, t0, sym, dp.amplitude_for_snr(snr, SIGMA, FS))
+    for ch, snr, k0, t0 in case["plan"]:
+        sym = wf.symbols(rng)
+        fa = k0 * wf.tone_hz
+        z += dp.fsk_iq(n, FS, case["demod"][ch] + fa, t0, sym, dp.amplitude_for_snr(snr, SIGMA, FS), wf)
         sigs.append((ch, snr, fa, t0, sym))
     if strong_carrier:   # an S9+40-like carrier elsewhere in the band, 70 dB above the noise in 2500 Hz
-        t = np.arange(N, dtype=np.float64)
-        z = z + dp.amplitude_for_snr(70.0, SIGMA, FS) * np.exp(2j * np.pi * ((-61000 * t) % FS) / FS)
+        t = np.arange(n, dtype=np.float64)
+        z += dp.amplitude_for_snr(70.0, SIGMA, FS) * np.exp(2j * np.pi * ((-61000 * t) % FS) / FS)
     iq = np.ascontiguousarray(np.stack([z.real, z.imag], axis=1), np.float32).reshape(-1)
     return iq, sigs
 
 
-def test_proxy_demodulates_the_reference_chain(port):
+@pytest.mark.parametrize("name", ["ft8", "ft4"])
+def test_proxy_demodulates_the_reference_chain(port, name):
     """The proxy itself: on the oracle's audio the strong signals come back without a symbol error at the nominal sync
     position, and the error count grows as the SNR falls -- i.e. it really is looking at the signals."""
-    iq, sigs = build_iq()
-    audio = port.slot(FS, DEMOD[0], iq, IQ_LEN, 0.9, af_size(15))["i16"]
+    case = CASES[name]
+    iq, sigs = build_iq(case)
+    audio = port.slot(FS, case["demod"][0], iq, IQ_LEN, 0.9, af_size(case["period"]))["i16"]
     errs = {}
     for ch, snr, fa, t0, sym in sigs:
         if ch != 0:
             continue
-        d = dp.demodulate(audio, fa, t0)
+        d = dp.demodulate(audio, fa, t0, case["wf"])
         errs[snr] = int((d["hard"] != sym).sum())
         if snr >= -10:
             assert d["sync"] == (0, 0) and errs[snr] == 0
-    assert errs[0.0] == 0 and errs[-10.0] == 0 and errs[-24.0] > errs[-16.0]
+    lo = min(errs)
+    assert errs[0.0] == 0 and errs[-10.0] == 0 and errs[lo] > errs[-16.0]
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("strong_carrier", [False, True], ids=["plain", "with_strong_carrier"])
 @pytest.mark.parametrize("mode", ["exact", "fast", "stft"])
-def test_demodulator_output_identical_to_reference(gpu, ref, mode, strong_carrier):
+@pytest.mark.parametrize("name", ["ft8", "ft4", "wspr"])
+def test_demodulator_output_identical_to_reference(gpu, ref, name, mode, strong_carrier):
     cw = gpu
-    iq, sigs = build_iq(strong_carrier)
+    case = CASES[name]
+    wf, demod, afs = case["wf"], case["demod"], af_size(case["period"])
+    if name == "wspr" and strong_carrier:
+        pytest.skip("the 120 s slot is covered without the carrier; the carrier case by the two short waveforms")
+    iq, sigs = build_iq(case, strong_carrier)
     m = {"exact": cw.MODE_EXACT, "fast": cw.MODE_FAST, "stft": cw.MODE_STFT}[mode]
     with cw.Receiver(0, FS, IQ_LEN, mode=m) as rx:
-        g = rx.add_group(15.0)
-        for f in DEMOD:
+        g = rx.add_group(case["period"])
+        for f in demod:
             rx.add_channel(g, f, 0.9)
         rx.push_iq(iq)
         out, wi = rx.end_slot_numpy(g)
         redone = rx.guard_stats(g)["redone"] if mode == "stft" else 0
-    want = [ref.slot(FS, f, iq, IQ_LEN, 0.9, af_size(15))["i16"] for f in DEMOD]
+    want = [ref.slot(FS, f, iq, IQ_LEN, 0.9, afs)["i16"] for f in demod]
     if mode == "exact":
-        for c in range(len(DEMOD)):
+        for c in range(len(demod)):
             assert np.array_equal(out[c], want[c])
     if mode == "stft" and strong_carrier:
         assert redone > 0        # the guard really handed the quiet channels' segments to the direct form
-    flips = 0
+    flips = total = 0
     for ch, snr, fa, t0, sym in sigs:
-        a = dp.demodulate(want[ch], fa, t0)
-        b = dp.demodulate(out[ch], fa, t0)
+        a = dp.demodulate(want[ch], fa, t0, wf)
+        b = dp.demodulate(out[ch], fa, t0, wf)
+        total += wf.nsym
         assert a["sync"] == b["sync"], (ch, snr)
         assert np.abs(a["soft"] - b["soft"]).max() <= SOFT_TOL, (ch, snr)
         assert np.abs(a["sync_grid"] - b["sync_grid"]).max() <= SOFT_TOL * a["sync_grid"].max()
@@ -95,7 +115,7 @@ def test_demodulator_output_identical_to_reference(gpu, ref, mode, strong_carrie
             top = np.sort(a["soft"][k])[::-1]
             assert top[0] - top[1] <= 2 * SOFT_TOL, (ch, snr, int(k), float(top[0] - top[1]))
             flips += 1
-        if not strong_carrier or snr >= FT8_THRESHOLD_DB:
+        if not strong_carrier or snr >= case["threshold"]:
             assert np.array_equal(a["hard"], b["hard"]), (ch, snr)
-    print(f"{mode}, strong carrier {strong_carrier}: {flips} of {79 * len(sigs)} hard decisions differ (ties only)")
+    print(f"{name} {mode}, strong carrier {strong_carrier}: {flips} of {total} hard decisions differ (ties only)")
     assert flips <= 2
