@@ -624,8 +624,8 @@ uint64_t slot_target_blocks(const cwsl_rx* rx, const Group& g) {
 }
 
 // CWSL_MODE_STFT uses the channelizer from this many channels per slot group on. Measured break-even on B200 at
-// 192 kHz: 64 channels x FT8 slot take 0.39 ms in the direct FAST kernel and 0.41 ms in the channelizer (whose FFT
-// side alone is 0.41 ms); 256 channels 1.27 vs 0.55 ms. CWSL_STFT_MIN_CHANNELS overrides.
+// 192 kHz: 64 channels x FT8 slot take 0.39 ms in the direct FAST kernel and 0.34 ms in the channelizer (whose FFT
+// side alone is 0.33 ms); 48 channels 0.29 vs 0.33 ms; 256 channels 1.27 vs 0.38 ms. CWSL_STFT_MIN_CHANNELS overrides.
 uint32_t stft_min_channels() {
     static const uint32_t v = [] {
         const char* e = std::getenv("CWSL_STFT_MIN_CHANNELS");

@@ -270,10 +270,19 @@ __global__ void __maxnreg__(kLaunchRegs)
         // local stage l of this CTA holds the slot-relative blocks kbase0 + HB*l .. +HB-1; batch `it` (its own new
         // samples are stage P0 + it) reads stages it .. it + P0
         const long long kbase0 = (long long)p.b0 + ((long long)s0 - P0) * HB;
-        auto issue_stage = [&](uint32_t l) {
-            long long m = ((long long)p.ring_off + kbase0 + (long long)l * HB) % (long long)p.ring_blocks;
+        // Stages are issued strictly in order, so the ring row of the next one is kept incrementally (one 64-bit
+        // modulo per launch instead of one per stage: the issuing lane's ~100-instruction division held up the whole
+        // of warp 0 -- and with it, through the batch barrier, all FFT warps -- for ~600 cycles per batch).
+        uint32_t next_row;
+        {
+            long long m = ((long long)p.ring_off + kbase0) % (long long)p.ring_blocks;
             if (m < 0) m += p.ring_blocks;  // (blocks before the slot: whatever the ring holds, masked below)
-            const uint32_t row = (uint32_t)m, slot = l % kIqStages;
+            next_row = (uint32_t)m;
+        }
+        auto issue_stage = [&](uint32_t l) {
+            const uint32_t row = next_row, slot = l % kIqStages;
+            next_row += (uint32_t)HB;
+            if (next_row >= p.ring_blocks) next_row -= p.ring_blocks;  // (HB <= 32 < 64 <= ring_blocks)
             const uint32_t dst = smem_u32(iq_s + (size_t)slot * HB * BS), bar_a = smem_u32(bars + slot);
             mbar_arrive_expect_tx(bar_a, kStageBytes);
             const uint32_t first = min((uint32_t)HB, p.ring_blocks - row);  // the IQ ring may wrap inside the stage
