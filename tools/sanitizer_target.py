@@ -22,6 +22,13 @@ for mode in (cw.MODE_FAST, cw.MODE_EXACT, cw.MODE_STFT):
             rx.push_iq(iq[b * IQ_LEN * 2:(b + 7) * IQ_LEN * 2])
         out, wi = rx.end_slot_numpy(g)
         print("mode", mode, "wi", wi, "checksum", int(out.astype(np.int64).sum()))
+        # second slot on the same handle through the packed hand-off (rows of write_index samples, 1-D copy)
+        for b in range(0, 42, 7):
+            rx.push_iq(iq[b * IQ_LEN * 2:(b + 7) * IQ_LEN * 2])
+        packed = np.zeros(len(freqs) * rx.group_af_size(g), np.int16)
+        wi = rx.end_slot_packed(g, packed)
+        rx.synchronize()
+        print("mode", mode, "packed wi", wi, "checksum", int(packed[:len(freqs) * wi].astype(np.int64).sum()))
 # the STFT guard's redo path: one carrier ~80 dB over the noise, so the quiet channels' segments are recomputed by the
 # indirect FAST launch (work lists built on the device, phases replayed from the anchors into the per-stream scratch)
 hdr = iq.copy()
