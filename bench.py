@@ -245,7 +245,19 @@ def run_b200(a):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # The communicator's first use prints "NCCL version ..." on stdout; stdout is reserved for the one JSON line,
+        # so the file descriptor points at stderr while NCCL comes up.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     MODES = {"stft": cw.MODE_STFT, "fast": cw.MODE_FAST, "exact": cw.MODE_EXACT}
     mode = MODES[a.mode]
