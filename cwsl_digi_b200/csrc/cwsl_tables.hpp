@@ -6,7 +6,7 @@
 //   low-pass prototype   source/LowPass.hpp:16-35   (double math, one rounding to float per tap)
 //   DC normalisation     source/SSBD.hpp:66-68      (sequential float sum, float divide)
 //   NCO tone / phase_inc source/SSBD.hpp:110-114    (float phase_delta, glibc cexpf)
-// tests/test_tables.py pins them bit-for-bit against oracle/_ref (the reference's own headers).
+// tests/test_capi_cpu.py (test_host_tables_bit_identical_to_reference, test_tables_property) pins them bit-for-bit against oracle/_ref (the reference's own headers).
 #pragma once
 
 #include <algorithm>

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "CWSL_DIGI_Types.hpp"
+#include "WsprSynth.hpp"
 
 class IqSource {
 public:
@@ -26,7 +27,8 @@ public:
     virtual bool readBlock(float* dst) = 0;
 };
 
-// Deterministic noise + carriers; unpaced (returns as fast as it is read).
+// Deterministic noise + carriers + M-FSK transmissions with valid codewords (WsprSynth.hpp); unpaced (returns as
+// fast as it is read).
 class SyntheticIqSource : public IqSource {
 public:
     struct Carrier {
@@ -37,6 +39,7 @@ public:
                       double sigma = 300.0, std::uint64_t seed = 20261017, std::uint64_t max_blocks = ~0ull)
         : fs_(fs), iq_len_(iq_len), lo_(lo), carriers_(std::move(carriers)), sigma_(sigma), state_(seed),
           max_blocks_(max_blocks) {}
+    void addBurst(FskBurst b) { bursts_.push_back(std::move(b)); }  // before the first readBlock()
     bool open(const std::string&) override { return true; }
     std::uint32_t sampleRate() const override { return fs_; }
     std::uint32_t blockInSamples() const override { return iq_len_; }
@@ -54,6 +57,17 @@ public:
                 const double cyc = std::fmod(f * static_cast<double>(n_ % fs_) / fs_, 1.0);
                 re += c.amplitude * std::cos(two_pi * cyc);
                 im += c.amplitude * std::sin(two_pi * cyc);
+            }
+            for (FskBurst& b : bursts_) {  // continuous phase: the frequency is integrated sample by sample
+                double t = static_cast<double>(n_) / fs_;
+                if (b.period_s > 0) t = std::fmod(t, b.period_s);
+                const double k = std::floor((t - b.t0_s) / b.symbol_s);
+                if (t < b.t0_s || k >= static_cast<double>(b.symbols.size())) continue;
+                const double f = b.rf_hz + b.tone_hz * b.symbols[static_cast<std::size_t>(k)] - static_cast<double>(lo_);
+                b.phase += f / fs_;
+                b.phase -= std::floor(b.phase);
+                re += b.amplitude * std::cos(two_pi * b.phase);
+                im += b.amplitude * std::sin(two_pi * b.phase);
             }
             dst[2 * i] = static_cast<float>(re);
             dst[2 * i + 1] = static_cast<float>(im);
@@ -80,6 +94,7 @@ private:
     std::uint32_t fs_, iq_len_;
     FrequencyHz lo_;
     std::vector<Carrier> carriers_;
+    std::vector<FskBurst> bursts_;
     double sigma_;
     std::uint64_t state_;
     std::uint64_t max_blocks_;

@@ -1,6 +1,8 @@
 // CPU-only unit tests of the host-side classes (no GPU call is made): decoder= grammar,
 // calibration arithmetic, mode/period table, WAV header bytes, DecoderPool hand-off, predicates.
 // Run by tests/test_host_cpu.py; exit code 0 = all passed.
+#include <array>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <sstream>
@@ -27,8 +29,59 @@ static bool throws(F f) {
     return false;
 }
 
+// "K1ABC FN42 37": the channel symbols printed in the WSPR protocol description (sync vector in the LSBs)
+static const char kWsprKat[] =
+    "330020001020131222100323133220200032012322002232110233210221321222033030301210212032132003323032203020201023"
+    "021112330231212221332000010320132222202332323320031222";
+
 int main(int argc, char** argv) {
+    // host_tests wspr CALL GRID DBM            -> the 162 channel symbols (tests/test_wspr_cpu.py compares encoders)
+    // host_tests wspriq OUT.f32 SECONDS SNR_DB -> SyntheticIqSource with one K1ABC transmission at LO + 1500 Hz
+    if (argc >= 5 && std::string(argv[1]) == "wspr") {
+        std::array<std::uint8_t, wspr::kSymbols> s{};
+        std::string why;
+        if (!wspr::encode(argv[2], argv[3], std::atoi(argv[4]), s, &why)) {
+            std::fprintf(stderr, "%s\n", why.c_str());
+            return 3;
+        }
+        for (auto v : s) std::putchar('0' + v);
+        std::putchar('\n');
+        return 0;
+    }
+    if (argc >= 5 && std::string(argv[1]) == "wspriq") {
+        const std::uint32_t fs = 192000, iq_len = 2048;
+        SyntheticIqSource src(fs, iq_len, 14100000, {}, 300.0, 20261017);
+        FskBurst b;
+        if (!makeWsprBurst("K1ABC", "FN42", 37, 14100000 - 4400 + 1500.0, amplitudeForSnr(std::atof(argv[4]), 300.0, fs), b)) return 3;
+        src.addBurst(b);
+        FILE* f = std::fopen(argv[2], "wb");
+        if (!f) return 3;
+        std::vector<float> blk(2 * iq_len);
+        const std::uint64_t nblk = static_cast<std::uint64_t>(std::atof(argv[3]) * fs / iq_len);
+        for (std::uint64_t i = 0; i < nblk && src.readBlock(blk.data()); ++i) std::fwrite(blk.data(), sizeof(float), blk.size(), f);
+        std::fclose(f);
+        return 0;
+    }
     const std::string tmp = argc > 1 ? argv[1] : "/tmp";
+
+    // ---- WSPR channel code (WsprSynth.hpp): known-answer test + rejections ----
+    {
+        std::array<std::uint8_t, wspr::kSymbols> s{};
+        EXPECT(wspr::encode("K1ABC", "FN42", 37, s));
+        bool same = true;
+        for (int i = 0; i < wspr::kSymbols; ++i) same = same && s[i] == kWsprKat[i] - '0';
+        EXPECT(same);
+        std::array<std::uint8_t, wspr::kSymbols> s2{};
+        EXPECT(wspr::encode(" k1abc ", "fn42", 37, s2) && s2 == s);           // case and padding do not matter
+        std::string why;
+        EXPECT(!wspr::encode("N0CALL", "FN20", 30, s2, &why) && !why.empty()); // digit would have to sit in 4th place
+        EXPECT(!wspr::encode("K1ABC", "FN4", 37, s2) && !wspr::encode("K1ABC", "ZZ42", 37, s2));
+        EXPECT(!wspr::encode("K1ABC", "FN42", 35, s2));                        // not a WSPR power level
+        FskBurst b;
+        EXPECT(makeWsprBurst("W1AW", "FN31", 30, 14097100.0, 10.0, b) && b.symbols.size() == 162 && b.period_s == 120.0);
+        EXPECT(std::fabs(b.rf_hz - (14097100.0 - 1.5 * 12000.0 / 8192.0)) < 1e-9);
+        EXPECT(std::fabs(amplitudeForSnr(0.0, 300.0, 192000.0) - std::sqrt(2.0 * 90000.0 * 2500.0 / 192000.0)) < 1e-9);
+    }
 
     // ---- periods (source/CWSL_DIGI.hpp:64-113) ----
     EXPECT(getRXPeriod("FT8") == 15.0f && getRXPeriod("FT4") == 7.5f && getRXPeriod("WSPR") == 120.0f);

@@ -22,6 +22,20 @@
 #include "cwsl_host.hpp"
 
 namespace {
+// The transmissions every WSPR decoder of the demo hears (audio frequency of the signal's centre, SNR in 2500 Hz,
+// start within the slot); tests/test_host_gpu.py expects exactly these messages back from the WAV hand-off.
+struct WsprDemoTx {
+    const char* call;
+    const char* grid;
+    int dbm;
+    double audio_hz, snr_db, t0_s;
+};
+const WsprDemoTx kWsprDemoTransmissions[] = {
+    {"K1ABC", "FN42", 37, 1500.0, -12.0, 1.0},
+    {"W1AW", "FN31", 30, 1440.0, -20.0, 1.3},
+    {"G4JNT", "IO90", 23, 1570.0, -24.0, 0.8},
+};
+
 // A slot clock in signal time: the receiver's reader thread asks the source for blocks; the source
 // fires predicates when the sample count crosses a period boundary (what waitForTime* does on the
 // wall clock, source/CWSL_DIGI.cpp:174-451).
@@ -230,12 +244,28 @@ int main(int argc, char** argv) {
     std::map<FrequencyHz, std::shared_ptr<Receiver>> receivers;
     std::map<FrequencyHz, std::set<float>> periods;
     std::map<FrequencyHz, std::vector<SyntheticIqSource::Carrier>> carriers;
+    std::map<FrequencyHz, std::vector<FskBurst>> bursts;
     float longest = 0;
     for (auto& d : cfg.decoders) {
         const FrequencyHz lo = (d.getFreqCalibrated() + 50000) / 100000 * 100000;
         periods[lo].insert(d.getTRPeriod());
-        carriers[lo].push_back({d.getFreqCalibrated() + 1500.0, 8000.0});
         longest = std::max(longest, d.getTRPeriod());
+        if (d.getMode() == "WSPR") {
+            // WSPR decoders hear three valid transmissions per 120 s slot (WsprSynth.hpp) instead of a plain carrier:
+            // what reaches wsprd through the WAV hand-off is decodable (tests/test_host_gpu.py decodes it)
+            for (const auto& tx : kWsprDemoTransmissions) {
+                FskBurst b;
+                std::string why;
+                if (!makeWsprBurst(tx.call, tx.grid, tx.dbm, d.getFreqCalibrated() + tx.audio_hz,
+                                   amplitudeForSnr(tx.snr_db, 300.0, 192000.0), b, tx.t0_s, &why)) {
+                    printer->err("WSPR demo transmission: " + why);
+                    return EXIT_FAILURE;
+                }
+                bursts[lo].push_back(b);
+            }
+            continue;
+        }
+        carriers[lo].push_back({d.getFreqCalibrated() + 1500.0, 8000.0});
     }
     const std::uint32_t fs = 192000, iq_len = 2048;
     const std::uint64_t max_blocks = static_cast<std::uint64_t>(slots * longest * fs / iq_len) + 2;
@@ -244,6 +274,7 @@ int main(int argc, char** argv) {
     for (auto& kv : periods) {
         preds[kv.first] = std::make_shared<SyncPredicates>();
         auto synth = std::make_unique<SyntheticIqSource>(fs, iq_len, kv.first, carriers[kv.first], 300.0, 20261017 + ridx, max_blocks);
+        for (const FskBurst& b : bursts[kv.first]) synth->addBurst(b);
         std::unique_ptr<IqSource> inner;
         std::string smname = "SYNTH" + std::to_string(kv.first / 1000) + "kHz";
         if (shmSource) {

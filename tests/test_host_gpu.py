@@ -5,7 +5,10 @@ and the IQ-block index of every slot edge, so each artefact is re-derived from t
   f2  transfermethod=shmem: what the jt9 stand-in finds in d2[] of the shared-memory block == the oracle's int16,
       parameters per mode, ipc[] handshake completed for every item; WSPR / JS8 still arrive as WAV files;
   f3  the same with the IQ coming through the CWSL shared-memory ring (producer thread -> POSIX segment ->
-      CwslShmSource -> pinned staging ring -> cwsl_rx_push_iq), no device synchronisation per block."""
+      CwslShmSource -> pinned staging ring -> cwsl_rx_push_iq), no device synchronisation per block;
+  f4  the WSPR decoders of the demo hear valid WSPR transmissions (WsprSynth.hpp): the WAV files wsprd would be
+      given decode -- with the blind decoder of tests/wspr_codec.py -- to exactly the transmitted messages, and to the
+      same decode set in all three arithmetic modes."""
 import glob
 import os
 import re
@@ -15,6 +18,7 @@ import subprocess
 import numpy as np
 import pytest
 
+import wspr_codec as wc
 from oracle.oracle import af_size
 
 pytestmark = pytest.mark.gpu
@@ -95,6 +99,18 @@ DECODERS_20M = [(14095600, "WSPR", 0.20), (14090000, "FT8", 0.90), (14080000, "F
                 (14076000, "JT65", 0.90), (14078000, "JS8", 0.90), (7074000, "FT8", 0.90), (7047500, "FT4", 0.90)]
 
 
+# what station_demo transmits to every WSPR decoder (kWsprDemoTransmissions): message -> (audio Hz, SNR dB, lag s)
+WSPR_DEMO = {"K1ABC FN42 37": (1500.0, -12.0, 0.0), "W1AW FN31 30": (1440.0, -20.0, 0.3), "G4JNT IO90 23": (1570.0, -24.0, -0.2)}
+
+
+def wspr_decode_sets(tmp_path):
+    """{wav name without the slot stamp: decode set} of the WSPR hand-off files of one demo run."""
+    out = {}
+    for w in sorted(glob.glob(os.path.join(tmp_path, "*_WSPR_*.wav"))):
+        out.setdefault(os.path.basename(w).split("_")[1], []).append(wc.decode_set(read_wav(w)))
+    return out
+
+
 def match_all(got, want, what):
     """Every artefact equals exactly one expected slot of its decoder, no slot is used twice, none is missing."""
     for key, vecs in got.items():
@@ -118,6 +134,20 @@ def test_wav_payload_equals_oracle_int16(station):
         got.setdefault((mode, int(freq)), []).append(a)
     assert {k[0] for k in got} == {"FT8", "FT4", "JT65", "JS8", "WSPR"}
     match_all(got, want, "WAV")
+
+
+def test_wspr_wav_decodes_to_the_transmitted_messages(station):
+    """f4 + f1: config.ini -> Receiver -> GPU front-end -> WAV for wsprd; the file decodes to the three valid
+    transmissions the synthetic source put on the air, at their frequencies, lags and SNRs."""
+    wavs = sorted(glob.glob(os.path.join(station["dir"], "*_WSPR_*.wav")))
+    assert wavs
+    for w in wavs:
+        got = {d["message"]: d for d in wc.decode(read_wav(w))}
+        assert set(got) == set(WSPR_DEMO), (w, sorted(got))
+        for msg, (fa, snr, lag) in WSPR_DEMO.items():
+            d = got[msg]
+            # (the slot edge falls on an IQ-block boundary: the lag is known to one block = 10.7 ms)
+            assert abs(d["freq_hz"] - fa) < 0.4 and abs(d["dt_s"] - lag) < 0.12 and abs(d["snr_db"] - snr) < 1.5, d
 
 
 def test_jt9_shared_memory_handoff_equals_oracle(tmp_path, station):
@@ -161,3 +191,4 @@ def test_station_demo_fast_modes_within_one_lsb(tmp_path, station, mode):
         assert best <= 1, (w, best)
         n += 1
     assert n == sum(len(v) for v in want.values())
+    assert wspr_decode_sets(tmp_path) == wspr_decode_sets(station["dir"])      # the decode gate, through the host mirror
