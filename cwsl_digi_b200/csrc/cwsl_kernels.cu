@@ -831,7 +831,10 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, cons
 // per receiver in the 64-receiver bench; alone, the 32-register shape (two groups per thread) is as fast as the
 // 48-register one (four groups). (A row-walking variant with prefetch.global.L2 stretched the channelizer by more than
 // it saved, 0.90 ms per receiver: rejected.)
-constexpr int kQuantThreads = 128, kQuantVec = 2, kQuantRegs = 32;
+#ifndef CWSL_QUANT_THREADS  // (A/B builds together with -DCWSL_CHAN_LAUNCH_REGS=...: what the channelizer leaves free)
+#define CWSL_QUANT_THREADS 128
+#endif
+constexpr int kQuantThreads = CWSL_QUANT_THREADS, kQuantVec = 2, kQuantRegs = 32;
 template <int kQuantVec, int kRegs>
 __global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
     const uint32_t c = blockIdx.y;
