@@ -824,17 +824,38 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, cons
 // Each operation is a separately rounded float op, as compiled from the reference with strict
 // IEEE flags. Samples past write_index are the zero tail: (int16)(0*factor + 0.5f) = 0.
 // ------------------------------------------------------------------------------------------
-// Each thread converts kQuantVec groups of 8 samples, all of its loads issued before the first conversion: the pass
-// is pure HBM traffic (0.19 ms per 1024-channel FT8 slot = 6.5 TB/s). It runs on the receiver's post stream under the
-// demodulation of the next receiver. 128 threads x 32 registers = 4096 registers per CTA is exactly what the STFT
-// channelizer (512 x 120) leaves free on an SM, so one CTA of this kernel runs beside it: 0.745 instead of 0.788 ms
-// per receiver in the 64-receiver bench; alone, the 32-register shape (two groups per thread) is as fast as the
-// 48-register one (four groups). (A row-walking variant with prefetch.global.L2 stretched the channelizer by more than
-// it saved, 0.90 ms per receiver: rejected.)
+// Each thread converts kQuantVec groups of 8 samples: the pass is pure HBM traffic (0.17 ms per 1024-channel FT8 slot
+// = 6.5 TB/s alone). It runs on the receiver's post stream under the demodulation of the next receiver. 128 threads x
+// 32 registers = 4096 registers per CTA is exactly what the STFT channelizer (512 x 120) leaves free on an SM, so one
+// CTA of this kernel runs beside it -- and there its rate is set by the bytes those 4096 registers keep in flight,
+// which is what paces the 64-receiver step (the post streams, not the channelizers, are its bottleneck). Interior CTAs
+// (every group full) therefore run a branch-free path; with four groups per thread ptxas keeps four 16-byte loads in
+// flight and refills as it converts (a software pipeline inside 32 registers, no spills), and a CTA lives twice as long
+// before its slot has to be refilled: 43.8 instead of 44.9 ms per 64-receiver step against two groups with per-group
+// predicates (three groups: 44.2; six: spills; 64-thread or 32-thread CTAs, 64 x 64 registers: 45.6 / 46.7 / 48.5 ms;
+// tools/runs/_run53...55.sh). Alone, all shapes take 0.170-0.173 ms. (A row-walking variant with prefetch.global.L2
+// stretched the channelizer by more than it saved, 0.90 ms per receiver: rejected.)
 #ifndef CWSL_QUANT_THREADS  // (A/B builds together with -DCWSL_CHAN_LAUNCH_REGS=...: what the channelizer leaves free)
 #define CWSL_QUANT_THREADS 128
 #endif
-constexpr int kQuantThreads = CWSL_QUANT_THREADS, kQuantVec = 2, kQuantRegs = 32;
+#ifndef CWSL_QUANT_VEC
+#define CWSL_QUANT_VEC 4
+#endif
+#ifndef CWSL_QUANT_PIPE
+#define CWSL_QUANT_PIPE 0
+#endif
+#ifndef CWSL_QUANT_REGS
+#define CWSL_QUANT_REGS 32
+#endif
+constexpr int kQuantThreads = CWSL_QUANT_THREADS, kQuantVec = CWSL_QUANT_VEC, kQuantRegs = CWSL_QUANT_REGS;
+__device__ __forceinline__ int4 quantise8(const float4& a, const float4& b, float factor) {
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    unsigned q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = (unsigned)(unsigned short)(short)__float2int_rz(__fadd_rn(__fmul_rn(x[e], factor), 0.5f));
+    return make_int4((int)(q[0] | (q[1] << 16)), (int)(q[2] | (q[3] << 16)), (int)(q[4] | (q[5] << 16)), (int)(q[6] | (q[7] << 16)));
+}
+
 template <int kQuantVec, int kRegs>
 __global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
     const uint32_t c = blockIdx.y;
@@ -850,44 +871,70 @@ __global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
     const uint32_t limit = min(pitch, p.af_size);  // packed rows end at write_index: nothing may be written behind it
     int16_t* __restrict__ dst = p.out + (size_t)c * pitch;
     const bool vec = (pitch % 8u == 0) && (p.af_stride % 4u == 0);
-    const uint32_t base = blockIdx.x * (kQuantThreads * 8u * kQuantVec) + threadIdx.x * 8u;
-    float4 a[kQuantVec], b[kQuantVec];
+    const uint32_t cta0 = blockIdx.x * (kQuantThreads * 8u * kQuantVec);
+    if (vec && cta0 + kQuantThreads * 8u * kQuantVec <= min(p.write_index, limit)) {
+        // interior CTA (all but the last one or two of a row): every group is full -- nothing but the loads, all
+        // issued before the first conversion, then the stores
+        const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src + cta0) + 2u * threadIdx.x;
+        int4* __restrict__ d4 = reinterpret_cast<int4*>(dst + cta0) + threadIdx.x;
+#if CWSL_QUANT_PIPE > 0
+        constexpr int D = CWSL_QUANT_PIPE;   // explicit pipeline: D groups in flight, refilled as they are converted
+        static_assert(kQuantVec % D == 0, "groups per thread must be a multiple of the pipeline depth");
+        float4 a[D], b[D];
 #pragma unroll
-    for (int v = 0; v < kQuantVec; ++v) {
-        const uint32_t i0 = base + v * (kQuantThreads * 8u);
-        if (vec && i0 + 8 <= p.write_index) {
-            a[v] = __ldcs(reinterpret_cast<const float4*>(src + i0));      // streaming: read exactly once
-            b[v] = __ldcs(reinterpret_cast<const float4*>(src + i0 + 4));
+        for (int d = 0; d < D; ++d) {
+            a[d] = __ldcs(s4 + d * (2 * kQuantThreads));
+            b[d] = __ldcs(s4 + d * (2 * kQuantThreads) + 1);
         }
+#pragma unroll 1
+        for (int v0 = 0; v0 < kQuantVec; v0 += D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const int4 pk = quantise8(a[d], b[d], factor);
+                if (v0 + D < kQuantVec) {
+                    a[d] = __ldcs(s4 + (v0 + d + D) * (2 * kQuantThreads));
+                    b[d] = __ldcs(s4 + (v0 + d + D) * (2 * kQuantThreads) + 1);
+                }
+                __stcs(d4 + (v0 + d) * kQuantThreads, pk);
+            }
+        }
+#else
+        float4 a[kQuantVec], b[kQuantVec];
+#pragma unroll
+        for (int v = 0; v < kQuantVec; ++v) {
+            a[v] = __ldcs(s4 + v * (2 * kQuantThreads));      // streaming: read exactly once
+            b[v] = __ldcs(s4 + v * (2 * kQuantThreads) + 1);
+        }
+#pragma unroll
+        for (int v = 0; v < kQuantVec; ++v) __stcs(d4 + v * kQuantThreads, quantise8(a[v], b[v], factor));
+#endif
+        return;
     }
-#pragma unroll
+    // the CTAs that hold the end of the written range / of the row: one group at a time
+#pragma unroll 1
     for (int v = 0; v < kQuantVec; ++v) {
-        const uint32_t i0 = base + v * (kQuantThreads * 8u);
+        const uint32_t i0 = cta0 + v * (kQuantThreads * 8u) + threadIdx.x * 8u;
         if (i0 >= limit) continue;
-        short q[8];
-        if (vec && i0 + 8 <= p.write_index) {
-            const float x[8] = {a[v].x, a[v].y, a[v].z, a[v].w, b[v].x, b[v].y, b[v].z, b[v].w};
+        if (vec) {
+            float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = a;
+            if (i0 + 8 <= p.write_index) {
+                a = __ldcs(reinterpret_cast<const float4*>(src + i0));
+                b = __ldcs(reinterpret_cast<const float4*>(src + i0 + 4));
+            } else if (i0 < p.write_index) {
+                float x[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) q[e] = (short)__float2int_rz(__fadd_rn(__fmul_rn(x[e], factor), 0.5f));
+                for (int e = 0; e < 8; ++e) x[e] = (i0 + e < p.write_index) ? src[i0 + e] : 0.0f;
+                a = make_float4(x[0], x[1], x[2], x[3]);
+                b = make_float4(x[4], x[5], x[6], x[7]);
+            }
+            __stcs(reinterpret_cast<int4*>(dst + i0), quantise8(a, b, factor));  // (0 * factor + 0.5f -> 0: the zero tail)
         } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const uint32_t i = i0 + e;
                 const float x = (i < p.write_index) ? src[i] : 0.0f;
-                q[e] = (short)__float2int_rz(__fadd_rn(__fmul_rn(x, factor), 0.5f));
+                if (i < limit) dst[i] = (short)__float2int_rz(__fadd_rn(__fmul_rn(x, factor), 0.5f));
             }
-        }
-        if (vec) {
-            int4 pk;
-            pk.x = (int)((unsigned short)q[0] | ((unsigned)(unsigned short)q[1] << 16));
-            pk.y = (int)((unsigned short)q[2] | ((unsigned)(unsigned short)q[3] << 16));
-            pk.z = (int)((unsigned short)q[4] | ((unsigned)(unsigned short)q[5] << 16));
-            pk.w = (int)((unsigned short)q[6] | ((unsigned)(unsigned short)q[7] << 16));
-            __stcs(reinterpret_cast<int4*>(dst + i0), pk);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (i0 + e < limit) dst[i0 + e] = q[e];
         }
     }
 }
