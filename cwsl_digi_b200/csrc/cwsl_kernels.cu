@@ -832,7 +832,7 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, cons
 // (every group full) therefore run a branch-free path; with four groups per thread ptxas keeps four 16-byte loads in
 // flight and refills as it converts (a software pipeline inside 32 registers, no spills), and a CTA lives twice as long
 // before its slot has to be refilled: 43.8 instead of 44.9 ms per 64-receiver step against two groups with per-group
-// predicates (three groups: 44.2; six: spills; 64-thread or 32-thread CTAs, 64 x 64 registers: 45.6 / 46.7 / 48.5 ms;
+// predicates (three groups: 44.2; six, or an explicit rolled pipeline of depth 2 / 3: spills; 64-thread or 32-thread CTAs, 64 x 64 registers: 45.6 / 46.7 / 48.5 ms;
 // tools/runs/_run53...55.sh). Alone, all shapes take 0.170-0.173 ms. (A row-walking variant with prefetch.global.L2
 // stretched the channelizer by more than it saved, 0.90 ms per receiver: rejected.)
 #ifndef CWSL_QUANT_THREADS  // (A/B builds together with -DCWSL_CHAN_LAUNCH_REGS=...: what the channelizer leaves free)
@@ -840,9 +840,6 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, cons
 #endif
 #ifndef CWSL_QUANT_VEC
 #define CWSL_QUANT_VEC 4
-#endif
-#ifndef CWSL_QUANT_PIPE
-#define CWSL_QUANT_PIPE 0
 #endif
 #ifndef CWSL_QUANT_REGS
 #define CWSL_QUANT_REGS 32
@@ -877,28 +874,6 @@ __global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
         // issued before the first conversion, then the stores
         const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src + cta0) + 2u * threadIdx.x;
         int4* __restrict__ d4 = reinterpret_cast<int4*>(dst + cta0) + threadIdx.x;
-#if CWSL_QUANT_PIPE > 0
-        constexpr int D = CWSL_QUANT_PIPE;   // explicit pipeline: D groups in flight, refilled as they are converted
-        static_assert(kQuantVec % D == 0, "groups per thread must be a multiple of the pipeline depth");
-        float4 a[D], b[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            a[d] = __ldcs(s4 + d * (2 * kQuantThreads));
-            b[d] = __ldcs(s4 + d * (2 * kQuantThreads) + 1);
-        }
-#pragma unroll 1
-        for (int v0 = 0; v0 < kQuantVec; v0 += D) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const int4 pk = quantise8(a[d], b[d], factor);
-                if (v0 + D < kQuantVec) {
-                    a[d] = __ldcs(s4 + (v0 + d + D) * (2 * kQuantThreads));
-                    b[d] = __ldcs(s4 + (v0 + d + D) * (2 * kQuantThreads) + 1);
-                }
-                __stcs(d4 + (v0 + d) * kQuantThreads, pk);
-            }
-        }
-#else
         float4 a[kQuantVec], b[kQuantVec];
 #pragma unroll
         for (int v = 0; v < kQuantVec; ++v) {
@@ -907,7 +882,6 @@ __global__ void __maxnreg__(kRegs) quantise_kernel(QuantLaunch p) {
         }
 #pragma unroll
         for (int v = 0; v < kQuantVec; ++v) __stcs(d4 + v * kQuantThreads, quantise8(a[v], b[v], factor));
-#endif
         return;
     }
     // the CTAs that hold the end of the written range / of the row: one group at a time
