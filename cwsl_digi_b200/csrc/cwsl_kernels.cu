@@ -834,7 +834,9 @@ cudaError_t launch_demod_fast(const DemodLaunch& p, uint32_t tiles_per_seg, cons
 // before its slot has to be refilled: 43.8 instead of 44.9 ms per 64-receiver step against two groups with per-group
 // predicates (three groups: 44.2; six, or an explicit rolled pipeline of depth 2 / 3: spills; 64-thread or 32-thread CTAs, 64 x 64 registers: 45.6 / 46.7 / 48.5 ms;
 // tools/runs/_run53...55.sh). Alone, all shapes take 0.170-0.173 ms. (A row-walking variant with prefetch.global.L2
-// stretched the channelizer by more than it saved, 0.90 ms per receiver: rejected.)
+// stretched the channelizer by more than it saved, 0.90 ms per receiver: rejected. One cp.async.bulk.prefetch.L2 per CTA for
+// the CTA 592 launches ahead -- no registers, no shared memory -- gives 43.2 instead of 43.9 ms per step but makes the pass
+// alone 8 % slower, 0.188 ms: duplicate requests once every CTA of the distance is already resident; not shipped.)
 #ifndef CWSL_QUANT_THREADS  // (A/B builds together with -DCWSL_CHAN_LAUNCH_REGS=...: what the channelizer leaves free)
 #define CWSL_QUANT_THREADS 128
 #endif
