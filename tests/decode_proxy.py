@@ -3,7 +3,7 @@
 north_star's last gate -- "the jt9/wsprd decode set must be identical" -- cannot be executed here: there is no
 jt9/wsprd in the image and the reference does not contain one (it spawns the WSJT-X binaries,
 source/DecoderPool.hpp:1007-1026). What CAN be executed is everything a decoder does before its channel code: find the
-signal and turn the audio into per-symbol tone decisions and soft metrics. This module builds FT8-, FT4- and WSPR-SHAPED
+signal and turn the audio into per-symbol tone decisions and soft metrics. This module builds FT8-, FT4-, JT65- and WSPR-SHAPED
 signals -- FT8: 8-FSK, 6.25 Hz tone spacing, 160 ms symbols, 79 symbols with the 7x7 Costas array 3,1,4,0,6,5,2 at symbols
 0, 36 and 72; FT4: 4-FSK, 20.83 Hz, 48 ms symbols, four 4x4 Costas arrays; WSPR: 4-FSK, 1.46 Hz, 0.683 s symbols, 162
 symbols with a sync bit in every symbol (the air-interface numbers printed in the WSJT-X user guide); the payload symbols
@@ -50,6 +50,22 @@ FT4 = Waveform("FT4-shaped", 4, 576, 103, {**_costas_at((0,), (0, 1, 3, 2)), **_
 # demodulator comparison), so only the tones {0,1} / {2,3} alternatives are constrained: modelled as 81 known symbols.
 _wspr_rng = np.random.default_rng(162)
 WSPR = Waveform("WSPR-shaped", 4, 8192, 162, {int(k): int(t) for k, t in zip(range(0, 162, 2), _wspr_rng.integers(0, 4, 81))})
+# JT65: 65-FSK + a sync tone, 2.69 Hz tone spacing, 0.372 s symbols (4096 samples at 11025 Hz = 4458 at 12 kHz; 4456 here, a multiple of 8), 126
+# symbols in a 60 s slot; the sync tone (tone 0) occupies 63 pseudo-randomly placed symbols, data tones start two
+# spacings above it. As for WSPR the positions are a stand-in of the same kind as the real pseudo-random vector.
+_jt65_rng = np.random.default_rng(65)
+JT65 = Waveform("JT65-shaped", 67, 4456, 126, {int(k): 0 for k in np.sort(_jt65_rng.choice(126, 63, replace=False))})
+_jt65_symbols = JT65.symbols
+
+
+def _jt65_data_symbols(rng):  # data symbols never use tone 0 / 1 (sync tone and its guard spacing)
+    sym = _jt65_symbols(rng)
+    data = np.array([k not in JT65.sync for k in range(JT65.nsym)])
+    sym[data] = rng.integers(2, JT65.ntones, int(data.sum()))
+    return sym
+
+
+JT65.symbols = _jt65_data_symbols
 NSYM, NSPS, TONE_HZ = FT8.nsym, FT8.nsps, FT8.tone_hz
 SYNC_AT = (0, 36, 72)
 

@@ -1,12 +1,12 @@
 """Executable stand-in for north_star's decode-set gate (see tests/decode_proxy.py for what it is and is not):
-FT8-, FT4- and WSPR-shaped M-FSK signals from 0 dB down to below each mode's decoding threshold (in 2500 Hz) go through
+FT8-, FT4-, JT65- and WSPR-shaped M-FSK signals from 0 dB down to below each mode's decoding threshold (in 2500 Hz) go through
 the reference chain (oracle) and through the GPU modes; a non-coherent demodulator -- sync search over time and frequency,
 per-symbol tone energies, hard decisions, soft metrics -- must produce the same output from both int16 buffers. EXACT
 hands over identical buffers (checked elsewhere, bit for bit); this is the evidence for FAST and STFT, whose buffers
 differ from the reference's by <= 1 LSB in ~0.1 % of the samples.
 
 Measured on B200: without a dominant carrier every sync position and every hard decision agrees in FAST and STFT, for
-all three waveforms (WSPR-shaped: a 120 s slot, 1.44 M steps of the drifting float NCO recurrence).
+all waveforms (JT65-shaped: 65 tones + sync tone in a 60 s slot; WSPR-shaped: a 120 s slot, 1.44 M steps of the drifting float NCO recurrence).
 With a carrier 70 dB (2500 Hz) over the noise elsewhere in the band, FAST -- and STFT, whose guard hands those channel
 segments to the FAST kernel -- differ from EXACT by the float32 rounding of that carrier's partial sums (~1e-7 of the
 band), and ONE decision of the FT8-shaped -24 dB signal (3 dB under FT8's threshold, 42 of its 79 decisions are wrong
@@ -31,6 +31,9 @@ CASES = {
     "ft4": dict(wf=dp.FT4, period=7.5, threshold=-17.5, demod=[-26000, 44000],
                 plan=[(0, 0.0, 30, 0.50), (0, -10.0, 60, 0.55), (0, -16.0, 90, 0.45), (0, -20.0, 115, 0.60),
                       (1, -14.0, 48, 0.52), (1, -18.0, 100, 0.48)]),
+    "jt65": dict(wf=dp.JT65, period=60.0, threshold=-25.0, demod=[-24000],
+                 plan=[(0, 0.0, 300, 1.0), (0, -10.0, 420, 1.3), (0, -16.0, 560, 0.8), (0, -24.0, 700, 1.1),
+                       (0, -28.0, 840, 0.9)]),
     "wspr": dict(wf=dp.WSPR, period=120.0, threshold=-31.0, demod=[-26000],
                  plan=[(0, -10.0, 960, 1.0), (0, -24.0, 1000, 1.5), (0, -30.0, 1040, 2.0), (0, -33.0, 1080, 1.2)]),
 }
@@ -56,7 +59,7 @@ def build_iq(case, strong_carrier=False):
     return iq, sigs
 
 
-@pytest.mark.parametrize("name", ["ft8", "ft4"])
+@pytest.mark.parametrize("name", ["ft8", "ft4", "jt65"])
 def test_proxy_demodulates_the_reference_chain(port, name):
     """The proxy itself: on the oracle's audio the strong signals come back without a symbol error at the nominal sync
     position, and the error count grows as the SNR falls -- i.e. it really is looking at the signals."""
@@ -78,13 +81,13 @@ def test_proxy_demodulates_the_reference_chain(port, name):
 @pytest.mark.gpu
 @pytest.mark.parametrize("strong_carrier", [False, True], ids=["plain", "with_strong_carrier"])
 @pytest.mark.parametrize("mode", ["exact", "fast", "stft"])
-@pytest.mark.parametrize("name", ["ft8", "ft4", "wspr"])
+@pytest.mark.parametrize("name", ["ft8", "ft4", "jt65", "wspr"])
 def test_demodulator_output_identical_to_reference(gpu, ref, name, mode, strong_carrier):
     cw = gpu
     case = CASES[name]
     wf, demod, afs = case["wf"], case["demod"], af_size(case["period"])
-    if name == "wspr" and strong_carrier:
-        pytest.skip("the 120 s slot is covered without the carrier; the carrier case by the two short waveforms")
+    if name in ("wspr", "jt65") and strong_carrier:
+        pytest.skip("the long slots are covered without the carrier; the carrier case by the two short waveforms")
     iq, sigs = build_iq(case, strong_carrier)
     m = {"exact": cw.MODE_EXACT, "fast": cw.MODE_FAST, "stft": cw.MODE_STFT}[mode]
     with cw.Receiver(0, FS, IQ_LEN, mode=m) as rx:
