@@ -248,7 +248,7 @@ def _stack_decode(soft: np.ndarray, max_nodes: int):
     l1 = np.log2(2.0 / (1.0 + np.exp(-a * soft))) - 0.5
     l0 = np.log2(2.0 / (1.0 + np.exp(+a * soft))) - 0.5
     met = (l0.tolist(), l1.tolist())
-    heap = [(0.0, 0, 0, 0)]         # (-metric, -depth tiebreak handled by tuple order, register, bits)
+    heap = [(0.0, 0, 0, 0)]         # (-metric, -depth, encoder register, decoded bits): best metric first, deeper on ties
     nodes = 0
     while heap and nodes < max_nodes:
         negm, depth, reg, bits = heapq.heappop(heap)
