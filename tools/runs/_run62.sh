@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 > gpurun_out/r2_bench62_n8.json 2> gpurun_out/r2_bench62_n8.err
+python -c "
+import json;d=[json.loads(l) for l in open('gpurun_out/r2_bench62_n8.json') if l.startswith('{')][-1];print(round(d['value']), d['ms_per_step'], d['e2e']['value'], d['n_gpus'], d['gpu_launches'], {k:v.get('value') for k,v in d['roofline_by_mode'].items()})"
+wc -l gpurun_out/r2_bench62_n8.json
