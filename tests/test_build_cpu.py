@@ -77,3 +77,21 @@ def test_channelizer_kernel_shape(cw):
     res = subprocess.run(["cuobjdump", "-res-usage", cw.lib_path()], capture_output=True, text=True, check=True).stdout
     regs = [int(m.group(1)) for m in re.finditer(r"demod_chan_kernel.*?\n.*?REG:(\d+)", res)]
     assert regs and max(regs) <= 120
+
+
+def test_quantise_kernel_fits_beside_the_channelizer(cw):
+    """The quantise pass runs in the 4096 registers per SM the channelizer leaves (128 threads x 32 registers): no
+    spills, streaming 128-bit loads and stores, and an interior path that issues at least four loads before its first
+    store (what keeps bytes in flight in that slot)."""
+    funcs = _sass(cw)
+    q = {k: v for k, v in funcs.items() if "quantise_kernel" in k}
+    assert len(q) == 1
+    body = next(iter(q.values()))
+    ops = _ops(body)
+    assert ops.count("LDL") + ops.count("STL") == 0
+    wide = [i for i in body if (i.startswith("LDG") or i.startswith("STG")) and ".128" in i]
+    first_store = next(n for n, i in enumerate(wide) if i.startswith("STG"))
+    assert first_store >= 4 and all(".EF" in i for i in wide[:first_store])    # evict-first: read exactly once
+    res = subprocess.run(["cuobjdump", "-res-usage", cw.lib_path()], capture_output=True, text=True, check=True).stdout
+    regs = [int(m.group(1)) for m in re.finditer(r"quantise_kernel.*?\n.*?REG:(\d+)", res)]
+    assert regs and max(regs) <= 32
