@@ -1,7 +1,7 @@
 // Dynamic-range guard of the STFT mode (CWSL_MODE_STFT).
 //
 // The channelizer's error in a channel is the rounding noise of one float32 FFT that all channels of the receiver
-// share: measured on B200 (tools/r2_probe.py, profiles/r2_guard_floor.json) 0.6e-7 (median) ... 1.9e-7 (worst channel)
+// share: measured on B200 (tools/r2_probe.py, profiles/r2_guard_floor_run1.json) 0.6e-7 (median) ... 1.9e-7 (worst channel)
 // of the rms of the WHOLE band on noise-like bands -- 10 butterfly stages + window + inter-pass twiddle, each ~0.5 ulp
 // -- and up to 5.8e-7 (-125 dB) when one or two carriers hold nearly all of the band's power, whatever the channel
 // itself holds. The direct form (source/SSBD.hpp:160-183, and the FAST kernel) keeps 15-17 dB more between a quiet
